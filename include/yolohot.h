@@ -1,0 +1,149 @@
+/* yolohot.h - C-ABI of libyolohot.so: the B200 (sm_100a) implementation of the YOLOv1
+ * post-processing / loss / mAP hot path of myungsanglee/Keras-Object-Detection.
+ *
+ * The reference has no FFI: its boundary is the Python call surface of
+ * yolo_v1/utils.py, loss.py and metric.py.  Each entry point below names the reference
+ * function (file:line, relative to the reference repo) whose arithmetic it replaces; the
+ * Python mirror of that surface (keras-object-detection_b200/yolohot/{utils,loss,metric}.py)
+ * binds these symbols with ctypes.  See INTEGRATION.md for the binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes; no C++/torch types.  `stream` is a cudaStream_t passed as
+ *     void* (NULL = legacy default stream).  All device entry points are asynchronous on
+ *     `stream` and run on the CUDA device that is current when they are called.
+ *   - all tensors are float32 / int32, C-contiguous, device-resident unless the name ends
+ *     in `_host`.  Layout of a prediction/label tensor is (N, S, S, C + 5*B) with the cell's
+ *     channels [class probs (C) | B x (conf, x, y, w, h)]  (yolo_v1/dataset.py:88-112).
+ *   - return value: YH_OK or a negative YH_ERR_*; the message is in yh_last_error()
+ *     (thread-local).  No exceptions, aborts or CPU fallbacks cross this boundary.
+ */
+#ifndef YOLOHOT_H_
+#define YOLOHOT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* exported symbol (the library is built with -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define YH_API __attribute__((visibility("default")))
+#else
+#define YH_API
+#endif
+
+#define YH_OK 0
+#define YH_ERR_ARG (-1)         /* null / shape / dtype / device / contiguity / alignment */
+#define YH_ERR_CUDA (-2)        /* a CUDA runtime call or launch failed */
+#define YH_ERR_UNSUPPORTED (-4) /* configuration outside the compiled limits (e.g. S*S > 256) */
+
+#define YH_MAX_CELLS 256        /* S*S limit of the NMS kernels (8 candidate slots per lane) */
+
+/* Forward declaration of the DLPack exchange struct (ABI of dlpack.h v0.8 / v1.0 legacy
+ * DLManagedTensor); full layout in yh_dlpack.h. */
+struct DLManagedTensor;
+
+/* ---- library ------------------------------------------------------------------------- */
+YH_API int yh_version(void);                 /* 1000*major + minor */
+YH_API const char *yh_last_error(void); /* thread-local, never NULL */
+YH_API int yh_device_info(int *sm_count, int *cc_major, int *cc_minor); /* of the current device */
+/* number of kernel launches issued by this library since load (all threads); bench.py's
+ * "gpu_launches" claim is counted from this. */
+YH_API int64_t yh_launch_count(void);
+
+/* ---- IoU: utils.py:9-43 intersection_over_union ---------------------------------------
+ * boxes1, boxes2: (n, 4) [cx, cy, w, h];  out: (n) - the reference's (...,4)->(...,1). */
+YH_API int yh_iou(const float *boxes1, const float *boxes2, int64_t n, float *out, void *stream);
+
+/* ---- decode: utils.py:152-218 decode_predictions --------------------------------------
+ * pred (n,S,S,C+5B) -> out_boxes (n, S*S, 6) rows [cls, conf, cx, cy, w, h]. */
+YH_API int yh_decode(const float *pred, int64_t n, int S, int B, int C, float *out_boxes, void *stream);
+
+/* ---- NMS: utils.py:79-114 non_max_suppression, batched --------------------------------
+ * boxes (n, M, 6) decoded rows; per image: keep conf > conf_thr, stable descending sort,
+ * greedy suppression of same-class boxes with IoU >= iou_thr.
+ * out_boxes (n, M, 6): the first out_count[i] rows of image i are the kept rows in pick
+ * order, the rest is left untouched.  out_keep_idx (n, M) (nullable): source row index of
+ * each kept row. */
+YH_API int yh_nms(const float *boxes, int64_t n, int M, float iou_thr, float conf_thr,
+           float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, void *stream);
+
+/* ---- fused decode + IoU + NMS: loop body of utils.py:470-480 --------------------------
+ * The graded throughput path.  Same outputs as yh_decode followed by yh_nms;
+ * out_keep_idx holds the source CELL index r*S+c of each kept row (nullable). */
+YH_API int yh_decode_nms(const float *pred, int64_t n, int S, int B, int C,
+                  float iou_thr, float conf_thr,
+                  float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, void *stream);
+
+/* Same, HOST buffers in and out (pageable or pinned): chunked H2D copy / kernel / D2H copy
+ * pipelined on internal streams of device `device`; returns after the results are on the
+ * host.  This is the call bench.py times for its end-to-end ("e2e") figure. */
+YH_API int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int B, int C,
+                       float iou_thr, float conf_thr,
+                       float *out_boxes_host, int32_t *out_count_host,
+                       int32_t *out_keep_idx_host /* nullable */, int device);
+
+/* ---- evaluator rows: utils.py:476-489 (prefix img_idx, append) ------------------------
+ * Compacts padded NMS output (n, M, 6) + count (n) into rows [img, cls, conf, cx,cy,w,h]
+ * appended at out_rows + 7 * (*row_cursor) ; image i gets img index img_base + i (as
+ * float32, like the reference).  row_cursor is a DEVICE int64 counter that the call
+ * advances by the number of rows written; rows beyond `out_capacity` rows are dropped and
+ * the cursor still advances (the caller checks it and re-runs after growing). */
+YH_API int yh_rows_append(const float *boxes, const int32_t *count, int64_t n, int M, int64_t img_base,
+                   float *out_rows, int64_t out_capacity, int64_t *row_cursor, void *stream);
+
+/* ---- loss: loss.py:120-215 YoloV1Loss.call (+ its autodiff backward) ------------------
+ * y_true, y_pred: (n_cells, C+5B) i.e. the (N,S,S,D) tensors flattened over cells.
+ * out_terms: 6 floats [xy, wh, obj, noobj, cls, total] (batch sums, loss.py:172-213).
+ * out_grad (nullable): d(total)/d(y_pred), same shape as y_pred. */
+YH_API int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells, int B, int C,
+            float lambda_coord, float lambda_noobj,
+            float *out_terms, float *out_grad, void *stream);
+
+/* ---- mAP: utils.py:303-456 mean_average_precision -------------------------------------
+ * Stage 1 (per image shard, no communication): greedy IoU matching of detections to
+ * ground truths.  true_rows (nt,7), pred_rows (np,7) rows [img, cls, conf, cx,cy,w,h].
+ * Writes, for the np detections in (class asc, conf desc, row asc) order:
+ *   out_keys (np) uint64 = class << 32 | ~orderable(conf)   (sort key of stage 2)
+ *   out_tp   (np) uint8  = 1 true positive / 0 false positive
+ * and out_gt_per_class (C) int32 = number of ground truths per class.
+ * Rows whose class is not an integer in [0, C) are ignored (the reference never selects
+ * them, utils.py:329-330) and get key = C << 32 | 0xffffffff (they sort after every class). */
+YH_API int yh_map_match(const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
+                 int C, float iou_thr,
+                 uint64_t *out_keys, uint8_t *out_tp, int32_t *out_gt_per_class, void *stream);
+
+/* Stage 2 (after the shards' records were concatenated in shard order, e.g. by an NCCL
+ * all-gather, and the per-class GT counts summed): stable sort by key, cumulative TP/FP,
+ * precision/recall, trapezoid AP per class (out_ap (C), nullable) and their mean
+ * (out_map (1)). */
+YH_API int yh_map_reduce(const uint64_t *keys, const uint8_t *tp, int64_t nrec,
+                  const int32_t *gt_per_class, int C, float *out_ap, float *out_map, void *stream);
+
+/* ---- DLPack front ends ----------------------------------------------------------------
+ * Same operations taking DLManagedTensor* (what `tensor.__dlpack__()` capsules hold, so
+ * torch / TF-Keras / CuPy tensors pass zero-copy).  They validate device (kDLCUDA, the
+ * current device), dtype, C-contiguity, shape and 4-byte alignment, then call the pointer
+ * entry points above.  A kDLCPU tensor is YH_ERR_ARG: there is no CPU fallback. */
+YH_API int yh_iou_dl(const struct DLManagedTensor *boxes1, const struct DLManagedTensor *boxes2,
+              struct DLManagedTensor *out, void *stream);
+YH_API int yh_decode_dl(const struct DLManagedTensor *pred, int B, int C,
+                 struct DLManagedTensor *out_boxes, void *stream);
+YH_API int yh_nms_dl(const struct DLManagedTensor *boxes, float iou_thr, float conf_thr,
+              struct DLManagedTensor *out_boxes, struct DLManagedTensor *out_count,
+              struct DLManagedTensor *out_keep_idx /* nullable */, void *stream);
+YH_API int yh_decode_nms_dl(const struct DLManagedTensor *pred, int B, int C,
+                     float iou_thr, float conf_thr,
+                     struct DLManagedTensor *out_boxes, struct DLManagedTensor *out_count,
+                     struct DLManagedTensor *out_keep_idx /* nullable */, void *stream);
+YH_API int yh_loss_dl(const struct DLManagedTensor *y_true, const struct DLManagedTensor *y_pred,
+               int B, int C, float lambda_coord, float lambda_noobj,
+               struct DLManagedTensor *out_terms, struct DLManagedTensor *out_grad /* nullable */,
+               void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLOHOT_H_ */

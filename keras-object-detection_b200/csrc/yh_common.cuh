@@ -1,0 +1,140 @@
+// yh_common.cuh - shared helpers of libyolohot (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "yolohot.h"
+
+namespace yh {
+
+// ---- host-side error plumbing (yh_abi.cu) -------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+void count_launch(int n = 1);
+
+#define YH_CUDA(call)                                                  \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return ::yh::cuda_fail(e_, #call);      \
+    } while (0)
+
+#define YH_REQUIRE(cond, ...)                                          \
+    do {                                                               \
+        if (!(cond)) {                                                 \
+            ::yh::set_error(__VA_ARGS__);                              \
+            return YH_ERR_ARG;                                         \
+        }                                                              \
+    } while (0)
+
+#define YH_LAUNCH_CHECK(name)                                          \
+    do {                                                               \
+        cudaError_t e_ = cudaGetLastError();                           \
+        if (e_ != cudaSuccess) return ::yh::cuda_fail(e_, name);       \
+        ::yh::count_launch();                                          \
+    } while (0)
+
+inline int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
+    }
+    return cached[dev];
+}
+
+#ifdef __CUDACC__
+// ---- exact float32 arithmetic of the reference -------------------------------------------
+// TF evaluates every op separately in float32 (round-to-nearest, no FMA contraction).  The
+// *_rn intrinsics are never contracted by nvcc, whatever --fmad says.
+
+// tf.clip_by_value(v, 0, 1)                                     (utils.py:39)
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+// utils.py:24-43.  a = boxes1 (cx, cy, w, h), b = boxes2.  Corners are (c -/+ w) / 2 (the
+// reference halves the centre too), extents clipped to [0, 1], |area|, +1e-6f last.
+__device__ __forceinline__ float iou_ref(float ax, float ay, float aw, float ah,
+                                         float bx, float by, float bw, float bh)
+{
+    const float x1n = __fmul_rn(__fsub_rn(ax, aw), 0.5f), y1n = __fmul_rn(__fsub_rn(ay, ah), 0.5f);
+    const float x1x = __fmul_rn(__fadd_rn(ax, aw), 0.5f), y1x = __fmul_rn(__fadd_rn(ay, ah), 0.5f);
+    const float x2n = __fmul_rn(__fsub_rn(bx, bw), 0.5f), y2n = __fmul_rn(__fsub_rn(by, bh), 0.5f);
+    const float x2x = __fmul_rn(__fadd_rn(bx, bw), 0.5f), y2x = __fmul_rn(__fadd_rn(by, bh), 0.5f);
+    const float iw = clip01(__fsub_rn(fminf(x1x, x2x), fmaxf(x1n, x2n)));
+    const float ih = clip01(__fsub_rn(fminf(y1x, y2x), fmaxf(y1n, y2n)));
+    const float inter = __fmul_rn(iw, ih);
+    const float a1 = fabsf(__fmul_rn(__fsub_rn(x1x, x1n), __fsub_rn(y1x, y1n)));
+    const float a2 = fabsf(__fmul_rn(__fsub_rn(x2x, x2n), __fsub_rn(y2x, y2n)));
+    const float den = __fadd_rn(__fsub_rn(__fadd_rn(a1, a2), inter), 1e-6f);
+    return __fdiv_rn(inter, den);
+}
+
+__device__ __forceinline__ float iou_ref(const float4 &a, const float4 &b)
+{
+    return iou_ref(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + bulk async copy (TMA, non-tensor form) ------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy; completion is signalled on `bar` as `bytes` of transaction count.
+// dst/src 16-byte aligned, bytes a multiple of 16.  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#endif  // __CUDACC__
+
+}  // namespace yh

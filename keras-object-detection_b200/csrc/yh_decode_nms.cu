@@ -1,0 +1,741 @@
+// yh_decode_nms.cu - K1..K4: grid decode, confidence filter + stable rank, per-class greedy
+// NMS (bitmask IoU + fixed-point greedy scan), element-wise IoU.  sm_100a.
+//
+// Reference arithmetic replaced (paths relative to the reference repo, yolo_v1/):
+//   decode  utils.py:152-218   NMS  utils.py:79-114   IoU  utils.py:9-43
+//   fused loop body of MeanAveragePrecision.update_state  utils.py:470-480
+//
+// Work decomposition (one warp owns one image at a time):
+//   A  each lane decodes cells lane, lane+32, ... (class argmax, best-confidence box,
+//      cell offset) and tests conf > thr; survivors are compacted with ballot/popc
+//   B  stable descending rank r_i = #{j : s_j > s_i} (+ #{j < i : s_j == s_i} only when a
+//      duplicate rank shows a tie exists); candidates are scattered to rank order in smem
+//   C  same-class lane masks with match.any, published per class in a small smem table
+//   D  every candidate tests only its same-class predecessors -> suppression bit words
+//   E  greedy keep flags by fixed-point iteration on ballots (exact: position q depends
+//      only on positions < q, so the iteration converges to the sequential result)
+//   F  kept rows are written in rank order; count per image
+// The fast path stages image tiles in shared memory with cp.async.bulk (TMA) through an
+// mbarrier ring filled by a producer warp; a direct-from-global kernel covers the tail,
+// unaligned inputs and grids too large for the ring.
+#include <algorithm>
+#include <cstdlib>
+
+#include "yh_common.cuh"
+
+namespace yh {
+
+struct NmsCfg {
+    int S, B, C, M, D;       // grid, boxes, classes, cells = S*S, channels = C + 5B
+    float inv_s;             // float32(1 / S)                         (utils.py:207)
+    float iou_thr, conf_thr;
+    int ws_bytes;            // per-warp workspace bytes
+    int tbl_rows;            // rows of the class table (C for fused, 32*NS for row input)
+};
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// per-warp workspace carve-up (MP = 32 * NS slots)
+template <int NS, bool kFloatCls>
+struct WarpWs {
+    static constexpr int MP = 32 * NS;
+    float4 *sbox;     // [MP]  boxes in rank order
+    float *sconf;     // [MP]
+    int *smeta;       // [MP]  (class key << 8) | source index
+    float *ckey;      // [MP + 4] compact candidate confidences (source order), -inf padded
+    float *cclsf;     // [MP]  compact float classes          (kFloatCls only)
+    float *sclsf;     // [MP]  float classes in rank order    (kFloatCls only)
+    unsigned *tbl;    // [tbl_rows * NS] class key -> lanes holding that class, per slot
+
+    __host__ __device__ static int bytes(int tbl_rows)
+    {
+        int b = MP * 16 + MP * 4 + MP * 4 + (MP + 4) * 4;
+        if (kFloatCls) b += MP * 8;
+        b += tbl_rows * NS * 4;
+        return (b + 15) & ~15;
+    }
+    __device__ explicit WarpWs(unsigned char *p)
+    {
+        sbox = reinterpret_cast<float4 *>(p);  p += MP * 16;
+        sconf = reinterpret_cast<float *>(p);  p += MP * 4;
+        smeta = reinterpret_cast<int *>(p);    p += MP * 4;
+        ckey = reinterpret_cast<float *>(p);   p += (MP + 4) * 4;
+        cclsf = sclsf = nullptr;
+        if (kFloatCls) {
+            cclsf = reinterpret_cast<float *>(p);  p += MP * 4;
+            sclsf = reinterpret_cast<float *>(p);  p += MP * 4;
+        }
+        tbl = reinterpret_cast<unsigned *>(p);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Phases B..F for one image held in registers: slot t of this lane is source index
+// lane + 32 t.  cls[t] is the class id (fused) or the raw float bits (kFloatCls).
+// Returns K (kept rows), identical on all lanes.
+// ------------------------------------------------------------------------------------------
+template <int NS, bool kFloatCls>
+__device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&box)[NS], const int (&cls)[NS],
+                                        const bool (&valid)[NS], const NmsCfg &cfg, WarpWs<NS, kFloatCls> &ws,
+                                        float *__restrict__ out_rows, int *__restrict__ out_idx)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // ---- A': compaction of the survivors (utils.py:95, strict >) ----
+    bool pass[NS];
+    int ci[NS];
+    int n = 0;
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        pass[t] = valid[t] && (conf[t] > cfg.conf_thr);
+        const unsigned b = __ballot_sync(FULL, pass[t]);
+        ci[t] = n + __popc(b & lt_mask);
+        n += __popc(b);
+        if (pass[t]) {
+            ws.ckey[ci[t]] = conf[t];
+            if (kFloatCls) ws.cclsf[ci[t]] = __int_as_float(cls[t]);
+        }
+    }
+    if (n == 0) return 0;
+    if (lane < 4) ws.ckey[n + lane] = -INFINITY;   // pad to a multiple of 4 for the float4 loop
+    __syncwarp();
+
+    // ---- B: stable descending rank (utils.py:98) ----
+    int r[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) r[t] = 0;
+    {
+        const float4 *k4p = reinterpret_cast<const float4 *>(ws.ckey);
+        const int n4 = (n + 3) >> 2;
+        for (int g = 0; g < n4; ++g) {
+            const float4 k = k4p[g];
+#pragma unroll
+            for (int t = 0; t < NS; ++t) {
+                const float c = conf[t];
+                r[t] += (k.x > c) + (k.y > c) + (k.z > c) + (k.w > c);
+            }
+        }
+    }
+    // a duplicate rank <=> equal confidences exist: only then pay for the tie-break pass
+    {
+#pragma unroll
+        for (int t = 0; t < NS; ++t)
+            if (pass[t]) ws.smeta[r[t]] = ci[t];
+        __syncwarp();
+        bool dup = false;
+#pragma unroll
+        for (int t = 0; t < NS; ++t)
+            if (pass[t]) dup |= (ws.smeta[r[t]] != ci[t]);
+        dup = __any_sync(FULL, dup);
+        __syncwarp();
+        if (dup) {
+            for (int j = 0; j < n; ++j) {
+                const float k = ws.ckey[j];
+#pragma unroll
+                for (int t = 0; t < NS; ++t) r[t] += (pass[t] && j < ci[t] && k == conf[t]) ? 1 : 0;
+            }
+        }
+    }
+    // class key: the class id itself, or (row input) the first candidate holding an equal class
+    int key[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) key[t] = kFloatCls ? ci[t] : cls[t];
+    if (kFloatCls) {
+        for (int j = n - 1; j >= 0; --j) {
+            const float f = ws.cclsf[j];
+#pragma unroll
+            for (int t = 0; t < NS; ++t)
+                if (pass[t] && f == __int_as_float(cls[t])) key[t] = j;
+        }
+    }
+    // scatter to rank order
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        if (pass[t]) {
+            const int q = r[t];
+            ws.sbox[q] = box[t];
+            ws.sconf[q] = conf[t];
+            ws.smeta[q] = (key[t] << 8) | (lane + 32 * t);
+            if (kFloatCls) ws.sclsf[q] = __int_as_float(cls[t]);
+        }
+    }
+    __syncwarp();
+
+    // ---- C: same-class masks.  Slot t of this lane now is rank position q = lane + 32 t ----
+    const int NT = (n + 31) >> 5;
+    bool act[NS];
+    int meta[NS];
+    float4 mb[NS];
+    unsigned lead = 0;
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int q = lane + 32 * t;
+        act[t] = q < n;
+        meta[t] = 0;
+        if (act[t]) {
+            meta[t] = ws.smeta[q];
+            mb[t] = ws.sbox[q];
+        }
+        if (t < NT) {
+            const unsigned m = __match_any_sync(FULL, act[t] ? (meta[t] >> 8) : (0x7f000000 + lane));
+            if (act[t] && (__ffs(m) - 1) == lane) {
+                ws.tbl[(meta[t] >> 8) * NS + t] = m;
+                lead |= 1u << t;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- D: suppression bits against same-class predecessors (utils.py:108) ----
+    unsigned supp[NS][NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+#pragma unroll
+        for (int t2 = 0; t2 < NS; ++t2) supp[t][t2] = 0u;
+    }
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        if (t < NT && act[t]) {
+            const unsigned *row = ws.tbl + (meta[t] >> 8) * NS;
+#pragma unroll
+            for (int t2 = 0; t2 <= t; ++t2) {
+                unsigned w = row[t2];
+                if (t2 == t) w &= lt_mask;
+                while (w) {
+                    const int b = __ffs(w) - 1;
+                    w &= w - 1;
+                    const float4 pb = ws.sbox[32 * t2 + b];
+                    const float v = iou_ref(pb, mb[t]);            // (chosen, later) as utils.py:108
+                    if (!(v < cfg.iou_thr)) supp[t][t2] |= 1u << b;
+                }
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NS; ++t)
+        if (lead & (1u << t)) ws.tbl[(meta[t] >> 8) * NS + t] = 0u;   // leave the table zeroed
+
+    // ---- E: greedy keep flags, fixed point of keep[q] = !any(supp[q] & keep) ----
+    bool alive[NS];
+    unsigned kw[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) alive[t] = act[t];
+    for (;;) {
+#pragma unroll
+        for (int t = 0; t < NS; ++t) kw[t] = (t < NT) ? __ballot_sync(FULL, alive[t]) : 0u;
+        bool ch = false;
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            if (act[t]) {
+                unsigned s = 0u;
+#pragma unroll
+                for (int t2 = 0; t2 <= t; ++t2) s |= supp[t][t2] & kw[t2];
+                const bool nv = (s == 0u);
+                ch |= (nv != alive[t]);
+                alive[t] = nv;
+            }
+        }
+        if (!__any_sync(FULL, ch)) break;
+    }
+
+    // ---- F: kept rows in pick order (utils.py:112) ----
+    int K = 0;
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        if (alive[t]) {
+            const int q = lane + 32 * t;
+            const int pos = K + __popc(kw[t] & lt_mask);
+            const float c = kFloatCls ? ws.sclsf[q] : static_cast<float>(meta[t] >> 8);   // utils.py:175
+            float2 *o = reinterpret_cast<float2 *>(out_rows + 6 * pos);
+            o[0] = make_float2(c, ws.sconf[q]);
+            o[1] = make_float2(mb[t].x, mb[t].y);
+            o[2] = make_float2(mb[t].z, mb[t].w);
+            if (out_idx) out_idx[pos] = meta[t] & 255;
+        }
+        K += __popc(kw[t]);
+    }
+    __syncwarp();   // workspace is reused by the next image
+    return K;
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase A: decode one cell (utils.py:173-208).  p may point to shared or global memory.
+// ------------------------------------------------------------------------------------------
+template <int CT, int BT>
+__device__ __forceinline__ void decode_cell(const float *__restrict__ p, const NmsCfg &cfg, float colf, float rowf,
+                                            int &cls, float &conf, float4 &box)
+{
+    float bx, by, bw, bh;
+    if constexpr (CT > 0 && BT > 0 && ((CT + 5 * BT) % 2 == 0)) {
+        constexpr int D = CT + 5 * BT;
+        float v[D];
+        const float2 *p2 = reinterpret_cast<const float2 *>(p);
+#pragma unroll
+        for (int i = 0; i < D / 2; ++i) {
+            const float2 x = p2[i];
+            v[2 * i] = x.x;
+            v[2 * i + 1] = x.y;
+        }
+        cls = 0;
+        float best = v[0];
+#pragma unroll
+        for (int j = 1; j < CT; ++j)
+            if (v[j] > best) { best = v[j]; cls = j; }            // first max (tf.argmax)
+        conf = v[CT]; bx = v[CT + 1]; by = v[CT + 2]; bw = v[CT + 3]; bh = v[CT + 4];
+#pragma unroll
+        for (int b = 1; b < BT; ++b) {
+            if (v[CT + 5 * b] > conf) {                            // first max over boxes (utils.py:183)
+                conf = v[CT + 5 * b]; bx = v[CT + 5 * b + 1]; by = v[CT + 5 * b + 2];
+                bw = v[CT + 5 * b + 3]; bh = v[CT + 5 * b + 4];
+            }
+        }
+    } else {
+        const int C = cfg.C, B = cfg.B;
+        cls = 0;
+        float best = p[0];
+        for (int j = 1; j < C; ++j) {
+            const float x = p[j];
+            if (x > best) { best = x; cls = j; }
+        }
+        int k = 0;
+        conf = p[C];
+        for (int b = 1; b < B; ++b) {
+            const float x = p[C + 5 * b];
+            if (x > conf) { conf = x; k = b; }
+        }
+        const float *q = p + C + 5 * k;
+        bx = q[1]; by = q[2]; bw = q[3]; bh = q[4];
+    }
+    box.x = __fmul_rn(cfg.inv_s, __fadd_rn(bx, colf));             // utils.py:207 (column)
+    box.y = __fmul_rn(cfg.inv_s, __fadd_rn(by, rowf));             // utils.py:208 (row)
+    box.z = bw;
+    box.w = bh;
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct kernel: one warp per image, cells read straight from global memory.
+// Any shape (S*S <= 32 NS), any alignment >= 4 B (8 B for the compile-time even-D path).
+// ------------------------------------------------------------------------------------------
+template <int NS, int CT, int BT>
+__global__ void __launch_bounds__(256) decode_nms_direct_kernel(const float *__restrict__ pred, int64_t n, NmsCfg cfg,
+                                                                float *__restrict__ out_boxes,
+                                                                int *__restrict__ out_count, int *__restrict__ out_idx)
+{
+    extern __shared__ uint4 smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    WarpWs<NS, false> ws(reinterpret_cast<unsigned char *>(smem_raw) + warp * cfg.ws_bytes);
+    for (int i = lane; i < cfg.tbl_rows * NS; i += 32) ws.tbl[i] = 0u;
+    __syncwarp();
+
+    float colf[NS], rowf[NS];
+    bool valid[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int cell = lane + 32 * t;
+        valid[t] = cell < cfg.M;
+        rowf[t] = static_cast<float>(cell / cfg.S);
+        colf[t] = static_cast<float>(cell % cfg.S);
+    }
+    for (int64_t img = static_cast<int64_t>(blockIdx.x) * wpb + warp; img < n;
+         img += static_cast<int64_t>(gridDim.x) * wpb) {
+        const float *base = pred + img * cfg.M * cfg.D;
+        float conf[NS];
+        float4 box[NS];
+        int cls[NS];
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            conf[t] = -INFINITY; cls[t] = 0; box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[t]) decode_cell<CT, BT>(base + (lane + 32 * t) * cfg.D, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
+        }
+        const int K = nms_warp<NS, false>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
+                                          out_idx ? out_idx + img * cfg.M : nullptr);
+        if (lane == 0) out_count[img] = K;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA kernel: persistent CTAs, warp 0 = producer (cp.async.bulk of T-image tiles into an
+// ST-deep mbarrier ring), W consumer warps in G = W/T groups; group g takes the CTA's tiles
+// g, g+G, ...; warp j of the group owns image j of the tile.  The stage is released as soon
+// as the image has been decoded into registers, before the NMS phases.
+// ------------------------------------------------------------------------------------------
+struct TmaCfg {
+    int T, W, ST;           // images per tile, consumer warps, stages
+    uint32_t tile_bytes;    // T * 4 * M * D, multiple of 16
+    int64_t n_tiles;
+};
+
+template <int NS, int CT, int BT>
+__global__ void __launch_bounds__(544, 1) decode_nms_tma_kernel(const float *__restrict__ pred, NmsCfg cfg, TmaCfg tc,
+                                                                float *__restrict__ out_boxes,
+                                                                int *__restrict__ out_count, int *__restrict__ out_idx)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *tiles = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(tc.ST) * tc.tile_bytes);
+    uint64_t *empty = full + tc.ST;
+    unsigned char *ws_base = reinterpret_cast<unsigned char *>(empty + tc.ST);
+    ws_base += (16 - (reinterpret_cast<uintptr_t>(ws_base) & 15)) & 15;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < tc.ST; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, tc.T);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int64_t my_tiles = (tc.n_tiles > blockIdx.x) ? (tc.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(pred);
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                const int s = static_cast<int>(it % tc.ST);
+                const uint32_t ph = static_cast<uint32_t>((it / tc.ST) & 1);
+                mbar_wait(empty + s, ph ^ 1u);
+                const int64_t tile = blockIdx.x + it * gridDim.x;
+                mbar_arrive_expect_tx(full + s, tc.tile_bytes);
+                bulk_g2s(tiles + static_cast<size_t>(s) * tc.tile_bytes, src + tile * tc.tile_bytes, tc.tile_bytes,
+                         full + s, pol);
+            }
+        }
+        return;
+    }
+
+    const int cw = warp - 1;              // consumer warp index
+    const int G = tc.W / tc.T;
+    const int g = cw / tc.T, j = cw % tc.T;
+    WarpWs<NS, false> ws(ws_base + cw * cfg.ws_bytes);
+    for (int i = lane; i < cfg.tbl_rows * NS; i += 32) ws.tbl[i] = 0u;
+    __syncwarp();
+
+    float colf[NS], rowf[NS];
+    bool valid[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int cell = lane + 32 * t;
+        valid[t] = cell < cfg.M;
+        rowf[t] = static_cast<float>(cell / cfg.S);
+        colf[t] = static_cast<float>(cell % cfg.S);
+    }
+    const int img_floats = cfg.M * cfg.D;
+    for (int64_t it = g; it < my_tiles; it += G) {
+        const int s = static_cast<int>(it % tc.ST);
+        const uint32_t ph = static_cast<uint32_t>((it / tc.ST) & 1);
+        mbar_wait(full + s, ph);
+        const float *base = reinterpret_cast<const float *>(tiles + static_cast<size_t>(s) * tc.tile_bytes) + j * img_floats;
+        float conf[NS];
+        float4 box[NS];
+        int cls[NS];
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            conf[t] = -INFINITY; cls[t] = 0; box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[t]) decode_cell<CT, BT>(base + (lane + 32 * t) * cfg.D, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);     // image is in registers: hand the slot back
+        const int64_t img = (blockIdx.x + it * gridDim.x) * tc.T + j;
+        const int K = nms_warp<NS, false>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
+                                          out_idx ? out_idx + img * cfg.M : nullptr);
+        if (lane == 0) out_count[img] = K;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// NMS over already decoded rows (n, M, 6): utils.py:79-114 as a batched call.
+// ------------------------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(256) nms_rows_kernel(const float *__restrict__ rows, int64_t n, NmsCfg cfg,
+                                                       float *__restrict__ out_boxes, int *__restrict__ out_count,
+                                                       int *__restrict__ out_idx)
+{
+    extern __shared__ uint4 smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    WarpWs<NS, true> ws(reinterpret_cast<unsigned char *>(smem_raw) + warp * cfg.ws_bytes);
+    for (int i = lane; i < cfg.tbl_rows * NS; i += 32) ws.tbl[i] = 0u;
+    __syncwarp();
+    for (int64_t img = static_cast<int64_t>(blockIdx.x) * wpb + warp; img < n;
+         img += static_cast<int64_t>(gridDim.x) * wpb) {
+        const float2 *base = reinterpret_cast<const float2 *>(rows + img * cfg.M * 6);
+        float conf[NS];
+        float4 box[NS];
+        int cls[NS];
+        bool valid[NS];
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            const int i = lane + 32 * t;
+            valid[t] = i < cfg.M;
+            conf[t] = -INFINITY; cls[t] = 0; box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[t]) {
+                const float2 a = base[3 * i], b = base[3 * i + 1], c = base[3 * i + 2];
+                cls[t] = __float_as_int(a.x);
+                conf[t] = a.y;
+                box[t] = make_float4(b.x, b.y, c.x, c.y);
+            }
+        }
+        const int K = nms_warp<NS, true>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
+                                         out_idx ? out_idx + img * cfg.M : nullptr);
+        if (lane == 0) out_count[img] = K;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// decode only (utils.py:152-218): one thread per cell, rows written as 3 x float2.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) decode_kernel(const float *__restrict__ pred, int64_t n_cells, NmsCfg cfg,
+                                                     float *__restrict__ out)
+{
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_cells;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int cell = static_cast<int>(i % cfg.M);
+        int cls;
+        float conf;
+        float4 box;
+        decode_cell<0, 0>(pred + i * cfg.D, cfg, static_cast<float>(cell % cfg.S), static_cast<float>(cell / cfg.S), cls,
+                          conf, box);
+        float2 *o = reinterpret_cast<float2 *>(out + i * 6);
+        o[0] = make_float2(static_cast<float>(cls), conf);
+        o[1] = make_float2(box.x, box.y);
+        o[2] = make_float2(box.z, box.w);
+    }
+}
+
+// element-wise IoU (utils.py:9-43), (n,4) x (n,4) -> (n)
+__global__ void __launch_bounds__(256) iou_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, int64_t n,
+                                                  float *__restrict__ out)
+{
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out[i] = iou_ref(a[i], b[i]);
+}
+__global__ void __launch_bounds__(256) iou_kernel_unaligned(const float *__restrict__ a, const float *__restrict__ b,
+                                                            int64_t n, float *__restrict__ out)
+{
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out[i] = iou_ref(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3], b[4 * i], b[4 * i + 1], b[4 * i + 2],
+                         b[4 * i + 3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+static int pick_ns(int M)
+{
+    const int need = (M + 31) / 32;
+    const int avail[] = {1, 2, 4, 7, 8};
+    for (int a : avail)
+        if (a >= need) return a;
+    return 0;
+}
+
+static int fill_cfg(NmsCfg &cfg, int S, int B, int C, float iou_thr, float conf_thr)
+{
+    YH_REQUIRE(S >= 1 && B >= 1 && C >= 1, "decode/nms: S, B, C must be >= 1 (got %d, %d, %d)", S, B, C);
+    if (S * S > YH_MAX_CELLS) {
+        set_error("decode/nms: S*S = %d exceeds the compiled limit %d", S * S, YH_MAX_CELLS);
+        return YH_ERR_UNSUPPORTED;
+    }
+    if (C >= (1 << 22)) {
+        set_error("decode/nms: C = %d too large", C);
+        return YH_ERR_UNSUPPORTED;
+    }
+    cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
+    cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
+    cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr;
+    cfg.ws_bytes = 0; cfg.tbl_rows = C;
+    return YH_OK;
+}
+
+template <int NS, int CT, int BT>
+static int launch_direct(const float *pred, int64_t n, NmsCfg cfg, float *out_boxes, int *out_count, int *out_idx,
+                         cudaStream_t st)
+{
+    cfg.ws_bytes = WarpWs<NS, false>::bytes(cfg.tbl_rows);
+    int wpb = 8;
+    while (wpb > 1 && static_cast<size_t>(wpb) * cfg.ws_bytes > 200 * 1024) wpb >>= 1;
+    const size_t smem = static_cast<size_t>(wpb) * cfg.ws_bytes;
+    if (smem > 227 * 1024) {
+        set_error("decode_nms: per-warp workspace %d B does not fit shared memory", cfg.ws_bytes);
+        return YH_ERR_UNSUPPORTED;
+    }
+    auto kern = decode_nms_direct_kernel<NS, CT, BT>;
+    YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 1;
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (n + wpb - 1) / wpb;
+    const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * per_sm));
+    kern<<<grid, wpb * 32, smem, st>>>(pred, n, cfg, out_boxes, out_count, out_idx);
+    YH_LAUNCH_CHECK("decode_nms_direct_kernel");
+    return YH_OK;
+}
+
+template <int NS, int CT, int BT>
+static int launch_fused(const float *pred, int64_t n, NmsCfg cfg, float *out_boxes, int *out_count, int *out_idx,
+                        cudaStream_t st)
+{
+    const int64_t img_bytes = 4ll * cfg.M * cfg.D;
+    int64_t done = 0;
+    // ---- TMA ring for the aligned bulk ----
+    const bool tma_on = env_int("YH_TMA", 1) != 0;
+    if (tma_on && (reinterpret_cast<uintptr_t>(pred) % 16 == 0) && img_bytes <= 12 * 1024) {
+        TmaCfg tc;
+        tc.W = env_int("YH_TMA_W", 16);
+        tc.T = env_int("YH_TMA_T", 8);
+        if (tc.W < 1 || tc.W > 16) tc.W = 16;
+        while (tc.T > 1 && ((tc.W % tc.T) != 0 || tc.T * img_bytes > 64 * 1024)) tc.T >>= 1;
+        if ((tc.T * img_bytes) % 16 == 0 && n >= tc.T) {
+            tc.tile_bytes = static_cast<uint32_t>(tc.T * img_bytes);
+            cfg.ws_bytes = WarpWs<NS, false>::bytes(cfg.tbl_rows);
+            const size_t fixed = 2 * 8 * 8 /*barriers*/ + 16 + static_cast<size_t>(tc.W) * cfg.ws_bytes + 128;
+            int stages = env_int("YH_TMA_STAGES", 4);
+            while (stages > 1 && fixed + static_cast<size_t>(stages) * tc.tile_bytes > 227 * 1024) --stages;
+            tc.ST = std::min(stages, 8);
+            tc.n_tiles = n / tc.T;
+            const size_t smem = fixed + static_cast<size_t>(tc.ST) * tc.tile_bytes;
+            if (tc.ST >= 2 && smem <= 227 * 1024) {
+                auto kern = decode_nms_tma_kernel<NS, CT, BT>;
+                YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                const int grid = static_cast<int>(std::min<int64_t>(tc.n_tiles, sm_count()));
+                kern<<<grid, 32 * (tc.W + 1), smem, st>>>(pred, cfg, tc, out_boxes, out_count, out_idx);
+                YH_LAUNCH_CHECK("decode_nms_tma_kernel");
+                done = tc.n_tiles * tc.T;
+            }
+        }
+    }
+    // ---- tail / fallback ----
+    if (done < n) {
+        return launch_direct<NS, CT, BT>(pred + done * cfg.M * cfg.D, n - done, cfg, out_boxes + done * cfg.M * 6,
+                                         out_count + done, out_idx ? out_idx + done * cfg.M : nullptr, st);
+    }
+    return YH_OK;
+}
+
+int decode_nms_device(const float *pred, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
+                      float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, cudaStream_t st)
+{
+    NmsCfg cfg;
+    int rc = fill_cfg(cfg, S, B, C, iou_thr, conf_thr);
+    if (rc != YH_OK) return rc;
+    YH_REQUIRE(n >= 0, "decode_nms: n < 0");
+    if (n == 0) return YH_OK;
+    YH_REQUIRE(pred && out_boxes && out_count, "decode_nms: null pointer");
+    YH_REQUIRE(reinterpret_cast<uintptr_t>(pred) % 8 == 0 && reinterpret_cast<uintptr_t>(out_boxes) % 8 == 0,
+               "decode_nms: pred and out_boxes must be 8-byte aligned");
+    const int ns = pick_ns(cfg.M);
+    if (ns == 2 && C == 20 && B == 2) return launch_fused<2, 20, 2>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
+    switch (ns) {
+        case 1: return launch_fused<1, 0, 0>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
+        case 2: return launch_fused<2, 0, 0>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
+        case 4: return launch_fused<4, 0, 0>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
+        case 7: return launch_fused<7, 0, 0>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
+        case 8: return launch_fused<8, 0, 0>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
+    }
+    set_error("decode_nms: unsupported cell count %d", cfg.M);
+    return YH_ERR_UNSUPPORTED;
+}
+
+template <int NS>
+static int launch_nms_rows(const float *rows, int64_t n, NmsCfg cfg, float *out_boxes, int *out_count, int *out_idx,
+                           cudaStream_t st)
+{
+    cfg.tbl_rows = 32 * NS;
+    cfg.ws_bytes = WarpWs<NS, true>::bytes(cfg.tbl_rows);
+    int wpb = 8;
+    while (wpb > 1 && static_cast<size_t>(wpb) * cfg.ws_bytes > 200 * 1024) wpb >>= 1;
+    const size_t smem = static_cast<size_t>(wpb) * cfg.ws_bytes;
+    auto kern = nms_rows_kernel<NS>;
+    YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 1;
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (n + wpb - 1) / wpb;
+    const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * per_sm));
+    kern<<<grid, wpb * 32, smem, st>>>(rows, n, cfg, out_boxes, out_count, out_idx);
+    YH_LAUNCH_CHECK("nms_rows_kernel");
+    return YH_OK;
+}
+
+}  // namespace yh
+
+using namespace yh;
+
+extern "C" int yh_decode_nms(const float *pred, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
+                             float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, void *stream)
+{
+    return decode_nms_device(pred, n, S, B, C, iou_thr, conf_thr, out_boxes, out_count, out_keep_idx,
+                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int yh_nms(const float *boxes, int64_t n, int M, float iou_thr, float conf_thr, float *out_boxes,
+                      int32_t *out_count, int32_t *out_keep_idx, void *stream)
+{
+    YH_REQUIRE(n >= 0 && M >= 1, "nms: bad sizes n=%lld M=%d", static_cast<long long>(n), M);
+    if (M > YH_MAX_CELLS) {
+        set_error("nms: M = %d exceeds the compiled limit %d", M, YH_MAX_CELLS);
+        return YH_ERR_UNSUPPORTED;
+    }
+    if (n == 0) return YH_OK;
+    YH_REQUIRE(boxes && out_boxes && out_count, "nms: null pointer");
+    YH_REQUIRE(reinterpret_cast<uintptr_t>(boxes) % 8 == 0 && reinterpret_cast<uintptr_t>(out_boxes) % 8 == 0,
+               "nms: boxes and out_boxes must be 8-byte aligned");
+    NmsCfg cfg;
+    cfg.S = 0; cfg.B = 0; cfg.C = 0; cfg.M = M; cfg.D = 6; cfg.inv_s = 0.f;
+    cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr; cfg.ws_bytes = 0; cfg.tbl_rows = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (pick_ns(M)) {
+        case 1: return launch_nms_rows<1>(boxes, n, cfg, out_boxes, out_count, out_keep_idx, st);
+        case 2: return launch_nms_rows<2>(boxes, n, cfg, out_boxes, out_count, out_keep_idx, st);
+        case 4: return launch_nms_rows<4>(boxes, n, cfg, out_boxes, out_count, out_keep_idx, st);
+        case 7: return launch_nms_rows<7>(boxes, n, cfg, out_boxes, out_count, out_keep_idx, st);
+        case 8: return launch_nms_rows<8>(boxes, n, cfg, out_boxes, out_count, out_keep_idx, st);
+    }
+    return YH_ERR_UNSUPPORTED;
+}
+
+extern "C" int yh_decode(const float *pred, int64_t n, int S, int B, int C, float *out_boxes, void *stream)
+{
+    NmsCfg cfg;
+    YH_REQUIRE(S >= 1 && B >= 1 && C >= 1 && n >= 0, "decode: bad sizes");
+    cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
+    cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
+    cfg.iou_thr = cfg.conf_thr = 0.f; cfg.ws_bytes = 0; cfg.tbl_rows = 0;
+    if (n == 0) return YH_OK;
+    YH_REQUIRE(pred && out_boxes, "decode: null pointer");
+    YH_REQUIRE(reinterpret_cast<uintptr_t>(out_boxes) % 8 == 0, "decode: out_boxes must be 8-byte aligned");
+    const int64_t cells = n * cfg.M;
+    const int grid = static_cast<int>(std::min<int64_t>((cells + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
+    decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred, cells, cfg, out_boxes);
+    YH_LAUNCH_CHECK("decode_kernel");
+    return YH_OK;
+}
+
+extern "C" int yh_iou(const float *boxes1, const float *boxes2, int64_t n, float *out, void *stream)
+{
+    YH_REQUIRE(n >= 0, "iou: n < 0");
+    if (n == 0) return YH_OK;
+    YH_REQUIRE(boxes1 && boxes2 && out, "iou: null pointer");
+    const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (reinterpret_cast<uintptr_t>(boxes1) % 16 == 0 && reinterpret_cast<uintptr_t>(boxes2) % 16 == 0)
+        iou_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(boxes1),
+                                         reinterpret_cast<const float4 *>(boxes2), n, out);
+    else
+        iou_kernel_unaligned<<<grid, 256, 0, st>>>(boxes1, boxes2, n, out);
+    YH_LAUNCH_CHECK("iou_kernel");
+    return YH_OK;
+}

@@ -1,0 +1,105 @@
+// yh_host.cu - host-buffer front end of the fused decode+NMS path: the call a reference user
+// makes with NumPy arrays (utils.py:588-620 `MeanAveragePrecisionNumpy.update_state`,
+// evaluate.py:40) and the call bench.py times end to end.
+//
+// The batch is cut into chunks; chunk c uses slot c % kSlots = {stream, device in/out
+// buffers}.  H2D copy, kernel and D2H copies of one chunk are ordered on its stream; the
+// slots' streams overlap, so the copy engines (one per direction) and the SMs all stay busy.
+#include <algorithm>
+#include <mutex>
+
+#include "yh_common.cuh"
+
+namespace yh {
+
+int decode_nms_device(const float *pred, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
+                      float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, cudaStream_t st);
+
+constexpr int kSlots = 3;
+
+struct HostCtx {
+    bool init = false;
+    cudaStream_t st[kSlots] = {};
+    float *d_in[kSlots] = {};
+    float *d_boxes[kSlots] = {};
+    int32_t *d_count[kSlots] = {};
+    int32_t *d_idx[kSlots] = {};
+    size_t cap_in = 0, cap_boxes = 0, cap_count = 0, cap_idx = 0;   // bytes per slot
+};
+
+static HostCtx g_ctx[64];
+static std::mutex g_mu;
+
+static int grow(void **p, size_t &cap, size_t need, bool &changed)
+{
+    (void)changed;
+    if (need <= cap && *p) return YH_OK;
+    if (*p) YH_CUDA(cudaFree(*p));
+    *p = nullptr;
+    YH_CUDA(cudaMalloc(p, need));
+    return YH_OK;
+}
+
+}  // namespace yh
+
+using namespace yh;
+
+extern "C" int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
+                                  float *out_boxes_host, int32_t *out_count_host, int32_t *out_keep_idx_host, int device)
+{
+    YH_REQUIRE(n >= 0 && S >= 1 && B >= 1 && C >= 1, "decode_nms_host: bad sizes");
+    YH_REQUIRE(device >= 0 && device < 64, "decode_nms_host: bad device %d", device);
+    if (n == 0) return YH_OK;
+    YH_REQUIRE(pred_host && out_boxes_host && out_count_host, "decode_nms_host: null pointer");
+    std::lock_guard<std::mutex> lock(g_mu);
+    int prev = 0;
+    YH_CUDA(cudaGetDevice(&prev));
+    YH_CUDA(cudaSetDevice(device));
+    struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+
+    const int64_t M = static_cast<int64_t>(S) * S, D = C + 5 * B;
+    const int64_t img_in = 4 * M * D, img_boxes = 4 * M * 6;
+    // chunk: ~96 MiB of input, a multiple of 16 images so every chunk keeps the TMA alignment
+    int64_t chunk = std::max<int64_t>(16, ((96ll << 20) / img_in) & ~15ll);
+    chunk = std::min<int64_t>(chunk, (n + 15) & ~15ll);
+
+    HostCtx &cx = g_ctx[device];
+    if (!cx.init) {
+        for (int s = 0; s < kSlots; ++s) YH_CUDA(cudaStreamCreateWithFlags(&cx.st[s], cudaStreamNonBlocking));
+        cx.init = true;
+    }
+    bool ch = false;
+    for (int s = 0; s < kSlots; ++s) {
+        int rc;
+        if ((rc = grow(reinterpret_cast<void **>(&cx.d_in[s]), cx.cap_in, chunk * img_in, ch)) != YH_OK) return rc;
+        if ((rc = grow(reinterpret_cast<void **>(&cx.d_boxes[s]), cx.cap_boxes, chunk * img_boxes, ch)) != YH_OK) return rc;
+        if ((rc = grow(reinterpret_cast<void **>(&cx.d_count[s]), cx.cap_count, chunk * 4, ch)) != YH_OK) return rc;
+        if (out_keep_idx_host)
+            if ((rc = grow(reinterpret_cast<void **>(&cx.d_idx[s]), cx.cap_idx, chunk * M * 4, ch)) != YH_OK) return rc;
+    }
+    cx.cap_in = std::max(cx.cap_in, static_cast<size_t>(chunk * img_in));
+    cx.cap_boxes = std::max(cx.cap_boxes, static_cast<size_t>(chunk * img_boxes));
+    cx.cap_count = std::max(cx.cap_count, static_cast<size_t>(chunk * 4));
+    if (out_keep_idx_host) cx.cap_idx = std::max(cx.cap_idx, static_cast<size_t>(chunk * M * 4));
+
+    int rc = YH_OK;
+    int64_t c = 0;
+    for (int64_t lo = 0; lo < n && rc == YH_OK; lo += chunk, ++c) {
+        const int s = static_cast<int>(c % kSlots);
+        const int64_t cnt = std::min(chunk, n - lo);
+        cudaStream_t st = cx.st[s];
+        YH_CUDA(cudaMemcpyAsync(cx.d_in[s], pred_host + lo * M * D, cnt * img_in, cudaMemcpyHostToDevice, st));
+        rc = decode_nms_device(cx.d_in[s], cnt, S, B, C, iou_thr, conf_thr, cx.d_boxes[s], cx.d_count[s],
+                               out_keep_idx_host ? cx.d_idx[s] : nullptr, st);
+        if (rc != YH_OK) break;
+        YH_CUDA(cudaMemcpyAsync(out_boxes_host + lo * M * 6, cx.d_boxes[s], cnt * img_boxes, cudaMemcpyDeviceToHost, st));
+        YH_CUDA(cudaMemcpyAsync(out_count_host + lo, cx.d_count[s], cnt * 4, cudaMemcpyDeviceToHost, st));
+        if (out_keep_idx_host)
+            YH_CUDA(cudaMemcpyAsync(out_keep_idx_host + lo * M, cx.d_idx[s], cnt * M * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kSlots; ++s) {
+        cudaError_t e = cudaStreamSynchronize(cx.st[s]);
+        if (e != cudaSuccess && rc == YH_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    return rc;
+}

@@ -1,0 +1,81 @@
+"""ctypes binding of libyolohot.so (C-ABI declared in include/yolohot.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the
+error is raised to the caller.  Nothing here imports the CPU oracle."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libyolohot.so")
+
+YH_OK, YH_ERR_ARG, YH_ERR_CUDA, YH_ERR_UNSUPPORTED = 0, -1, -2, -4
+
+_lib = None
+
+# every symbol include/yolohot.h declares (tests/test_abi.py checks the two stay in sync)
+SYMBOLS = (
+    "yh_version", "yh_last_error", "yh_device_info", "yh_launch_count",
+    "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_host", "yh_rows_append",
+    "yh_loss", "yh_map_match", "yh_map_reduce",
+    "yh_iou_dl", "yh_decode_dl", "yh_nms_dl", "yh_decode_nms_dl", "yh_loss_dl",
+)
+
+
+class YoloHotError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libyolohot.so once.  Raises if it was not built (run __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise YoloHotError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  yolohot has no CPU fallback.")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, f, i, i64 = C.c_void_p, C.c_float, C.c_int, C.c_int64
+    L.yh_version.restype = i
+    L.yh_last_error.restype = C.c_char_p
+    L.yh_launch_count.restype = i64
+    L.yh_device_info.argtypes = [C.POINTER(i)] * 3
+    L.yh_iou.argtypes = [vp, vp, i64, vp, vp]
+    L.yh_decode.argtypes = [vp, i64, i, i, i, vp, vp]
+    L.yh_nms.argtypes = [vp, i64, i, f, f, vp, vp, vp, vp]
+    L.yh_decode_nms.argtypes = [vp, i64, i, i, i, f, f, vp, vp, vp, vp]
+    L.yh_decode_nms_host.argtypes = [vp, i64, i, i, i, f, f, vp, vp, vp, i]
+    L.yh_rows_append.argtypes = [vp, vp, i64, i, i64, vp, i64, vp, vp]
+    L.yh_loss.argtypes = [vp, vp, i64, i, i, f, f, vp, vp, vp]
+    L.yh_map_match.argtypes = [vp, i64, vp, i64, i, f, vp, vp, vp, vp]
+    L.yh_map_reduce.argtypes = [vp, vp, i64, vp, i, vp, vp, vp]
+    L.yh_iou_dl.argtypes = [vp, vp, vp, vp]
+    L.yh_decode_dl.argtypes = [vp, i, i, vp, vp]
+    L.yh_nms_dl.argtypes = [vp, f, f, vp, vp, vp, vp]
+    L.yh_decode_nms_dl.argtypes = [vp, i, i, f, f, vp, vp, vp, vp]
+    L.yh_loss_dl.argtypes = [vp, vp, i, i, f, f, vp, vp, vp]
+    for s in SYMBOLS:
+        fn = getattr(L, s)
+        if s not in ("yh_version", "yh_last_error", "yh_launch_count"):
+            fn.restype = i
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    """Turn a negative return code into the exception the reference surface would raise."""
+    if rc == YH_OK:
+        return
+    msg = lib().yh_last_error().decode("utf-8", "replace")
+    text = f"{what}: {msg}" if what else msg
+    if rc == YH_ERR_ARG:
+        raise ValueError(text)
+    if rc == YH_ERR_UNSUPPORTED:
+        raise NotImplementedError(text)
+    raise YoloHotError(text)
+
+
+def launch_count():
+    return int(lib().yh_launch_count())

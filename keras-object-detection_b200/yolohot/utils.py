@@ -1,0 +1,337 @@
+"""Drop-in mirror of the reference's yolo_v1/utils.py hot-path surface on libyolohot.
+
+Same names, positional order and defaults as the reference (file:line = reference repo):
+  intersection_over_union(boxes1, boxes2)                               utils.py:9-43
+  non_max_suppression(boxes, iou_threshold=0.5, conf_threshold=0.4)     utils.py:79-114
+  decode_predictions(predictions, num_classes, num_boxes=2)             utils.py:152-218
+  mean_average_precision(true_boxes, pred_boxes, num_classes, iou_threshold=0.5)   utils.py:303-456
+  MeanAveragePrecision(num_classes, num_boxes=2)                        utils.py:459-496
+  *_numpy / MeanAveragePrecisionNumpy twins                             utils.py:46-76, 117-149, 221-277, 499-620
+plus the names the stale metric.py imports (get_all_bboxes, non_max_suppression_2,
+mean_average_precision_2; bodies in tmp.py:96-157, 440-595) and one additive call,
+decode_nms(), the batched fused path.
+
+Inputs may be torch CUDA tensors (zero-copy via DLPack), anything exposing __dlpack__, TF
+tensors, or host array-likes (copied to the current CUDA device).  Results come back in
+the producer's kind.  There is no CPU implementation behind any of these names."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._tensor import DL, as_device_f32, dl, give_back, ptr, require_cuda, stream_ptr
+
+__all__ = [
+    "intersection_over_union", "intersection_over_union_numpy",
+    "non_max_suppression", "non_max_suppression_numpy", "non_max_suppression_2",
+    "decode_predictions", "decode_predictions_numpy", "get_all_bboxes", "decode_nms",
+    "mean_average_precision", "mean_average_precision_numpy", "mean_average_precision_2",
+    "MeanAveragePrecision", "MeanAveragePrecisionNumpy",
+]
+
+
+# --------------------------------------------------------------------------- IoU
+def intersection_over_union(boxes1, boxes2):
+    """utils.py:9-43: element-wise IoU of [cx, cy, w, h] boxes, (...,4),(...,4) -> (...,1)."""
+    a, kind = as_device_f32(boxes1)
+    b, _ = as_device_f32(boxes2, a.device)
+    if a.shape != b.shape:   # the reference broadcasts through TF; expand explicitly
+        a, b = torch.broadcast_tensors(a, b)
+        a, b = a.contiguous(), b.contiguous()
+    if a.shape[-1] != 4:
+        raise ValueError(f"intersection_over_union: last dimension must be 4, got {tuple(a.shape)}")
+    out = torch.empty(a.shape[:-1] + (1,), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        ha, hb, ho = DL(a), DL(b), DL(out)
+        _lib.check(_lib.lib().yh_iou_dl(ha.ptr, hb.ptr, ho.ptr, stream_ptr(a.device)), "intersection_over_union")
+    return give_back(out, kind)
+
+
+def intersection_over_union_numpy(boxes1, boxes2):
+    """utils.py:46-76 twin: NumPy in, NumPy out, same device path."""
+    return intersection_over_union(np.asarray(boxes1, np.float32), np.asarray(boxes2, np.float32))
+
+
+# ------------------------------------------------------------------------ decode
+def _grid_shape(p, num_classes, num_boxes):
+    if p.dim() != 4 or p.shape[1] != p.shape[2] or p.shape[3] != num_classes + 5 * num_boxes:
+        raise ValueError(f"expected (N, S, S, {num_classes + 5 * num_boxes}) predictions, got {tuple(p.shape)}")
+    return int(p.shape[0]), int(p.shape[1])
+
+
+def decode_predictions(predictions, num_classes, num_boxes=2):
+    """utils.py:152-218: (N,S,S,C+5B) -> (N,S*S,6) rows [class_idx, confidence, cx, cy, w, h].
+    S is taken from the tensor (the reference hard-codes 7, utils.py:184,200-216)."""
+    p, kind = as_device_f32(predictions)
+    n, S = _grid_shape(p, num_classes, num_boxes)
+    out = torch.empty((n, S * S, 6), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        hp, ho = DL(p), DL(out)
+        _lib.check(_lib.lib().yh_decode_dl(hp.ptr, int(num_boxes), int(num_classes), ho.ptr, stream_ptr(p.device)),
+                   "decode_predictions")
+    return give_back(out, kind)
+
+
+def decode_predictions_numpy(predictions, num_classes, num_boxes=2):
+    """utils.py:221-277 twin (the reference's own twin is batch-1 only and float64-leaky)."""
+    return decode_predictions(np.asarray(predictions, np.float32), num_classes, num_boxes)
+
+
+def get_all_bboxes(out, grid=7, num_classes=20):
+    """tmp.py:96-157 (imported by the stale metric.py:7): decode with B=2."""
+    res = decode_predictions(out, num_classes, 2)
+    if int(res.shape[1]) != grid * grid:
+        raise ValueError(f"get_all_bboxes: tensor grid {int(round(res.shape[1] ** 0.5))} != grid={grid}")
+    return res
+
+
+# --------------------------------------------------------------------------- NMS
+def _nms_device(b, iou_threshold, conf_threshold, want_idx=False):
+    """b: (N,M,6) CUDA float32 -> padded (N,M,6), count (N,) int32, optional keep_idx (N,M)."""
+    n, M = int(b.shape[0]), int(b.shape[1])
+    out = torch.zeros((n, M, 6), dtype=torch.float32, device=b.device)
+    cnt = torch.empty((n,), dtype=torch.int32, device=b.device)
+    kidx = torch.full((n, M), -1, dtype=torch.int32, device=b.device) if want_idx else None
+    with torch.cuda.device(b.device):
+        hb, ho, hc, hk = DL(b), DL(out), DL(cnt), dl(kidx)
+        _lib.check(_lib.lib().yh_nms_dl(hb.ptr, float(iou_threshold), float(conf_threshold), ho.ptr, hc.ptr, ptr(hk),
+                                        stream_ptr(b.device)), "non_max_suppression")
+    return out, cnt, kidx
+
+
+def non_max_suppression(boxes, iou_threshold=0.5, conf_threshold=0.4):
+    """utils.py:79-114: one image's (M,6) rows -> the (K,6) kept rows in pick order.
+    A batched (N,M,6) input returns a list of N such tensors."""
+    b, kind = as_device_f32(boxes)
+    if b.dim() == 2 and b.shape[-1] == 6:
+        out, cnt, _ = _nms_device(b.unsqueeze(0), iou_threshold, conf_threshold)
+        return give_back(out[0, :int(cnt.item())], kind)
+    if b.dim() == 3 and b.shape[-1] == 6:
+        out, cnt, _ = _nms_device(b, iou_threshold, conf_threshold)
+        counts = cnt.tolist()
+        return [give_back(out[i, :k], kind) for i, k in enumerate(counts)]
+    raise ValueError(f"non_max_suppression: expected (M, 6) or (N, M, 6) boxes, got {tuple(b.shape)}")
+
+
+def non_max_suppression_numpy(boxes, iou_threshold=0.5, conf_threshold=0.4):
+    """utils.py:117-149 twin."""
+    return non_max_suppression(np.asarray(boxes, np.float32), iou_threshold, conf_threshold)
+
+
+def non_max_suppression_2(boxes, iou_threshold=0.5, conf_threshold=0.4):
+    """Name imported by the stale metric.py:7,77; same contract as non_max_suppression."""
+    return non_max_suppression(boxes, iou_threshold, conf_threshold)
+
+
+def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_threshold=0.4,
+               return_index=False, out=None):
+    """Fused, batched loop body of utils.py:470-480 (decode + per-image NMS).
+
+    Returns (boxes (N,S*S,6), count (N,) int32[, keep_idx (N,S*S) int32]): the first count[i]
+    rows of image i are its kept rows in pick order; rows past that are unspecified unless
+    `out` buffers were zeroed by the caller.  Host array-likes go through the pipelined
+    host entry point (yh_decode_nms_host) and come back as NumPy."""
+    L = _lib.lib()
+    if not isinstance(predictions, torch.Tensor) and not hasattr(predictions, "__dlpack__") or isinstance(predictions, np.ndarray):
+        require_cuda()
+        p = np.ascontiguousarray(np.asarray(predictions, dtype=np.float32))
+        if p.ndim != 4 or p.shape[1] != p.shape[2] or p.shape[3] != num_classes + 5 * num_boxes:
+            raise ValueError(f"expected (N, S, S, {num_classes + 5 * num_boxes}) predictions, got {p.shape}")
+        n, S = p.shape[0], p.shape[1]
+        boxes = np.zeros((n, S * S, 6), np.float32)
+        cnt = np.zeros((n,), np.int32)
+        kidx = np.full((n, S * S), -1, np.int32) if return_index else None
+        _lib.check(L.yh_decode_nms_host(p.ctypes.data, n, S, int(num_boxes), int(num_classes), float(iou_threshold),
+                                        float(conf_threshold), boxes.ctypes.data, cnt.ctypes.data,
+                                        kidx.ctypes.data if return_index else None, torch.cuda.current_device()),
+                   "decode_nms")
+        return (boxes, cnt, kidx) if return_index else (boxes, cnt)
+    p, kind = as_device_f32(predictions)
+    n, S = _grid_shape(p, num_classes, num_boxes)
+    if out is not None:
+        boxes, cnt = out[0], out[1]
+        kidx = out[2] if (return_index and len(out) > 2) else None
+    else:
+        boxes = torch.empty((n, S * S, 6), dtype=torch.float32, device=p.device)
+        cnt = torch.empty((n,), dtype=torch.int32, device=p.device)
+        kidx = torch.empty((n, S * S), dtype=torch.int32, device=p.device) if return_index else None
+    with torch.cuda.device(p.device):
+        hp, hb, hc, hk = DL(p), DL(boxes), DL(cnt), dl(kidx)
+        _lib.check(L.yh_decode_nms_dl(hp.ptr, int(num_boxes), int(num_classes), float(iou_threshold),
+                                      float(conf_threshold), hb.ptr, hc.ptr, ptr(hk), stream_ptr(p.device)), "decode_nms")
+    if return_index:
+        return give_back(boxes, kind), give_back(cnt, kind), give_back(kidx, kind)
+    return give_back(boxes, kind), give_back(cnt, kind)
+
+
+# --------------------------------------------------------------------------- mAP
+def map_match(true_rows, pred_rows, num_classes, iou_threshold=0.5):
+    """Stage 1 of the mAP (yh_map_match): device rows -> (keys u64 as int64, tp uint8, gt_per_class int32)."""
+    t, p = true_rows, pred_rows
+    dev = p.device
+    nt, npred = int(t.shape[0]), int(p.shape[0])
+    keys = torch.empty((npred,), dtype=torch.int64, device=dev)
+    tp = torch.empty((npred,), dtype=torch.uint8, device=dev)
+    gtc = torch.empty((num_classes,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().yh_map_match(t.data_ptr(), nt, p.data_ptr(), npred, int(num_classes), float(iou_threshold),
+                                           keys.data_ptr(), tp.data_ptr(), gtc.data_ptr(), stream_ptr(dev)), "map_match")
+    return keys, tp, gtc
+
+
+def map_reduce(keys, tp, gt_per_class, num_classes):
+    """Stage 2 of the mAP (yh_map_reduce): records -> (mAP 0-d tensor, AP per class)."""
+    dev = gt_per_class.device
+    ap = torch.empty((num_classes,), dtype=torch.float32, device=dev)
+    m = torch.empty((1,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().yh_map_reduce(keys.data_ptr(), tp.data_ptr(), int(keys.shape[0]), gt_per_class.data_ptr(),
+                                            int(num_classes), ap.data_ptr(), m.data_ptr(), stream_ptr(dev)), "map_reduce")
+    return m[0], ap
+
+
+def mean_average_precision(true_boxes, pred_boxes, num_classes, iou_threshold=0.5, return_ap=False):
+    """utils.py:303-456: rows [img_idx, class_idx, confidence, cx, cy, w, h] -> scalar mAP.
+
+    When torch.distributed is initialised with more than one rank, each rank passes the rows
+    of ITS image shard (image indices only need to be unique within a rank) and every rank
+    returns the global value: the per-shard records are all-gathered in rank order and the
+    per-class GT counts all-reduced (yolohot.dist), then reduced identically everywhere."""
+    t, kind = as_device_f32(true_boxes)
+    p, _ = as_device_f32(pred_boxes, t.device)
+    t = t.reshape(-1, 7)
+    p = p.reshape(-1, 7)
+    keys, tp, gtc = map_match(t, p, num_classes, iou_threshold)
+    from . import dist as _dist
+    if _dist.world_size() > 1:
+        keys, tp, gtc = _dist.gather_records(keys, tp, gtc)
+    m, ap = map_reduce(keys, tp, gtc, num_classes)
+    if kind == "numpy":
+        m = np.float32(m.item())
+        ap = ap.cpu().numpy()
+    elif kind == "tf":
+        m, ap = give_back(m, kind), give_back(ap, kind)
+    return (m, ap) if return_ap else m
+
+
+def mean_average_precision_numpy(true_boxes, pred_boxes, num_classes, iou_threshold=0.5):
+    """utils.py:499-585 twin."""
+    return mean_average_precision(np.asarray(true_boxes, np.float32), np.asarray(pred_boxes, np.float32),
+                                  num_classes, iou_threshold)
+
+
+def mean_average_precision_2(true_bboxes, pred_bboxes, iou_threshold=0.5, num_classes=20):
+    """tmp.py:440-595 signature (imported by the stale metric.py:7,99)."""
+    return mean_average_precision(true_bboxes, pred_bboxes, num_classes, iou_threshold)
+
+
+class MeanAveragePrecision:
+    """utils.py:459-496.  reset_states() / update_state(y_true, y_pred) / result().
+
+    State is append-only device row buffers + a device cursor instead of the reference's
+    O(total^2) re-concatenation (utils.py:484-489); `all_true_boxes_variable` /
+    `all_pred_boxes_variable` materialise the (rows, 7) views on demand.  The reference
+    semantics are kept: ground truth goes through NMS too (utils.py:480), thresholds are the
+    hard-coded (0.5, 0.4), reset_states() only rewinds the image counter and the next
+    update overwrites the buffers (utils.py:467-468, 484-486)."""
+
+    _nms_true = True
+    _as_numpy = False
+
+    def __init__(self, num_classes, num_boxes=2):
+        self._num_classes = int(num_classes)
+        self._num_boxes = int(num_boxes)
+        self.img_idx = 0
+        self._dev = None
+        self._rows = {}      # 'true' / 'pred' -> [buffer (cap,7), cursor (1,) int64, host upper bound]
+
+    # -- state helpers
+    def _ensure(self, name, dev, extra):
+        st = self._rows.get(name)
+        if st is None:
+            cap = max(1024, 2 * extra)
+            st = [torch.empty((cap, 7), dtype=torch.float32, device=dev),
+                  torch.zeros((1,), dtype=torch.int64, device=dev), 0]
+            self._rows[name] = st
+        if st[2] + extra > st[0].shape[0]:
+            used = int(st[1].item())             # sync only when the bound says we might overflow
+            st[2] = used
+            if used + extra > st[0].shape[0]:
+                new = torch.empty((max(2 * st[0].shape[0], used + 2 * extra), 7), dtype=torch.float32, device=dev)
+                new[:used] = st[0][:used]
+                st[0] = new
+        return st
+
+    def _view(self, name):
+        st = self._rows.get(name)
+        if st is None:
+            t = torch.full((1, 7), -1.0, dtype=torch.float32)            # utils.py:461-462 initial value
+        else:
+            t = st[0][:int(st[1].item())]
+        return t.cpu().numpy() if self._as_numpy else t
+
+    @property
+    def all_true_boxes_variable(self):
+        return self._view("true")
+
+    @property
+    def all_pred_boxes_variable(self):
+        return self._view("pred")
+
+    # -- reference surface
+    def reset_states(self):
+        self.img_idx = 0
+
+    def update_state(self, y_true, y_pred):
+        yt, _ = as_device_f32(y_true)
+        yp, _ = as_device_f32(y_pred, yt.device)
+        n, S = _grid_shape(yp, self._num_classes, self._num_boxes)
+        if tuple(yt.shape) != tuple(yp.shape):
+            raise ValueError(f"update_state: y_true {tuple(yt.shape)} and y_pred {tuple(yp.shape)} differ")
+        dev = yp.device
+        self._dev = dev
+        if self.img_idx == 0:                       # utils.py:484-486: first image overwrites
+            for st in self._rows.values():
+                st[1].zero_()
+                st[2] = 0
+        L = _lib.lib()
+        M = S * S
+        for name, y in (("pred", yp), ("true", yt)):
+            if name == "true" and not self._nms_true:   # stale metric.py:81: conf > 0.4 only, cell order
+                boxes = decode_predictions(y, self._num_classes, self._num_boxes)
+                boxes, cnt = _filter_rows(boxes, 0.4)
+            else:                                    # utils.py:475 / :480
+                boxes, cnt = decode_nms(y, self._num_classes, self._num_boxes, 0.5, 0.4)
+            st = self._ensure(name, dev, n * M)
+            with torch.cuda.device(dev):
+                _lib.check(L.yh_rows_append(boxes.data_ptr(), cnt.data_ptr(), n, M, int(self.img_idx),
+                                            st[0].data_ptr(), int(st[0].shape[0]), st[1].data_ptr(), stream_ptr(dev)),
+                           "update_state")
+            st[2] += n * M
+        self.img_idx += n                            # utils.py:491
+
+    def result(self):
+        t = self._view("true")
+        p = self._view("pred")
+        return mean_average_precision(t, p, self._num_classes)       # utils.py:496
+
+
+class MeanAveragePrecisionNumpy(MeanAveragePrecision):
+    """utils.py:588-620 twin: NumPy in/out on the same device path."""
+    _as_numpy = True
+
+    def result(self):
+        return np.float32(float(super().result()))
+
+
+def _filter_rows(boxes, conf_threshold):
+    """metric.py:81 (stale evaluator): rows with conf > thr, cell order kept.  Implemented as an
+    NMS whose IoU threshold can never fire (IoU <= 1 < 2) followed by restoring cell order."""
+    n, M = int(boxes.shape[0]), int(boxes.shape[1])
+    out, cnt, kidx = _nms_device(boxes, 2.0, conf_threshold, want_idx=True)
+    order = torch.argsort(torch.where(kidx >= 0, kidx, torch.full_like(kidx, M)), dim=1, stable=True)
+    out = torch.gather(out, 1, order.unsqueeze(-1).expand(-1, -1, 6)).contiguous()
+    return out, cnt

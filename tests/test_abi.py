@@ -1,0 +1,102 @@
+"""CPU tests of the boundary: libyolohot.so loads, exports every symbol include/yolohot.h
+declares, validates arguments before touching the GPU, and never falls back to a CPU path."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "yolohot.h")).read()
+    return sorted(set(re.findall(r"YH_API[^;(]*?\b(yh_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from yolohot import _lib
+    assert header_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    from yolohot import _lib
+    L = _lib.lib()
+    for s in header_symbols():
+        assert hasattr(L, s), s
+    assert L.yh_version() >= 1
+    assert isinstance(L.yh_last_error(), bytes)
+
+
+def test_argument_errors_need_no_gpu():
+    from yolohot import _lib
+    L = _lib.lib()
+    assert L.yh_iou(None, None, -1, None, None) == _lib.YH_ERR_ARG
+    assert b"n < 0" in L.yh_last_error()
+    assert L.yh_decode_nms(None, 4, 7, 2, 20, 0.5, 0.4, None, None, None, None) == _lib.YH_ERR_ARG
+    assert L.yh_decode_nms(None, 4, 17, 2, 20, 0.5, 0.4, None, None, None, None) == _lib.YH_ERR_UNSUPPORTED
+    assert L.yh_nms(None, 1, 300, 0.5, 0.4, None, None, None, None) == _lib.YH_ERR_UNSUPPORTED
+    assert L.yh_loss(None, None, 10, 2, 20, 5.0, 0.5, None, None, None) == _lib.YH_ERR_ARG
+    with pytest.raises(ValueError):
+        _lib.check(_lib.YH_ERR_ARG, "x")
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.YH_ERR_UNSUPPORTED, "x")
+    with pytest.raises(_lib.YoloHotError):
+        _lib.check(_lib.YH_ERR_CUDA, "x")
+
+
+def test_cpu_tensor_is_rejected_not_computed():
+    """kDLCPU input -> YH_ERR_ARG: there is no CPU fallback behind the DLPack front ends."""
+    from yolohot import _lib
+    from yolohot._tensor import DL
+    L = _lib.lib()
+    a = torch.zeros(8, 4)
+    out = torch.zeros(8, 1)
+    rc = L.yh_iou_dl(DL(a).ptr, DL(a).ptr, DL(out).ptr, None)
+    assert rc == _lib.YH_ERR_ARG and b"no CPU fallback" in L.yh_last_error()
+    p = torch.zeros(2, 7, 7, 30)
+    rc = L.yh_decode_nms_dl(DL(p).ptr, 2, 20, 0.5, 0.4, DL(torch.zeros(2, 49, 6)).ptr,
+                            DL(torch.zeros(2, dtype=torch.int32)).ptr, None, None)
+    assert rc == _lib.YH_ERR_ARG
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_public_surface_fails_loudly_without_gpu():
+    from yolohot import loss, utils
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        utils.decode_predictions(np.zeros((1, 7, 7, 30), np.float32), 20, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        utils.decode_nms(np.zeros((1, 7, 7, 30), np.float32), 20, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        loss.YoloV1Loss()(np.zeros((1, 7, 7, 30), np.float32), np.zeros((1, 7, 7, 30), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "keras-object-detection_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no CPU oracle", "").replace("the CPU oracle", "").lower() or f == "_lib.py", (dirpath, f)
+
+
+def test_reference_module_names_resolve():
+    """`from utils import ...`, `from loss import ...`, `from metric import ...` as the reference's scripts do."""
+    import importlib.util
+    d = os.path.join(ROOT, "keras-object-detection_b200", "yolo_v1")
+    names = {"utils": ["intersection_over_union", "non_max_suppression", "decode_predictions", "mean_average_precision",
+                       "MeanAveragePrecision", "MeanAveragePrecisionNumpy", "get_all_bboxes", "non_max_suppression_2",
+                       "mean_average_precision_2", "decode_predictions_numpy", "non_max_suppression_numpy",
+                       "intersection_over_union_numpy", "mean_average_precision_numpy"],
+             "loss": ["YoloV1Loss"], "metric": ["MeanAveragePrecision", "MeanAveragePrecision2"]}
+    for mod, syms in names.items():
+        spec = importlib.util.spec_from_file_location(f"_shim_{mod}", os.path.join(d, mod + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        for s in syms:
+            assert hasattr(m, s), (mod, s)
+    from yolohot.loss import YoloV1Loss
+    l = YoloV1Loss()
+    assert (l.num_classes, l.num_boxes, l.lambda_coord, l.lambda_noobj, l.name) == (20, 2, 5, 0.5, "YoloV1Loss")

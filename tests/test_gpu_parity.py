@@ -1,0 +1,362 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the public surface / the C-ABI,
+against the oracle on identical seeded inputs.  Bars (BASELINE.json north_star):
+kept indices, class labels and kept counts bit-exact; decoded coordinates bit-exact here
+(the kernels keep the reference's float32 op order; the stated bar is 1e-5 relative);
+loss within 1e-5 relative; mAP within 1e-6."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport
+from oracle import yolo_oracle as O
+from tests import fixtures as F
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _cuda(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _check_nms(got, want, what=""):
+    gb, gc, gk = (x.cpu().numpy() if isinstance(x, torch.Tensor) else x for x in got)
+    wb, wc, wk = want
+    assert np.array_equal(gc, wc), f"{what}: kept counts differ at {np.nonzero(gc != wc)[0][:8]}"
+    m = np.arange(wb.shape[1])[None, :] < wc[:, None]
+    assert np.array_equal(np.where(m, gk, -1), np.where(m, wk, -1)), f"{what}: kept indices differ"
+    assert np.array_equal(gb[m], wb[m]), f"{what}: kept rows differ"
+
+
+# ------------------------------------------------------------------------------- IoU
+def test_iou_bit_exact(dev):
+    from yolohot import utils as yu
+    rng = np.random.default_rng(0)
+    a = rng.normal(0.4, 0.3, (4097, 4)).astype(F32)
+    b = rng.normal(0.4, 0.3, (4097, 4)).astype(F32)
+    got = yu.intersection_over_union(_cuda(a, dev), _cuda(b, dev))
+    assert got.shape == (4097, 1)
+    assert np.array_equal(got.cpu().numpy(), O.intersection_over_union(a, b))
+    # the reference's other call shapes: (N,S,S,4) (loss.py:128) and two 4-vectors (utils.py:108)
+    a4, b4 = a[:4096].reshape(4, 32, 32, 4), b[:4096].reshape(4, 32, 32, 4)
+    assert np.array_equal(yu.intersection_over_union(_cuda(a4, dev), _cuda(b4, dev)).cpu().numpy(),
+                          O.intersection_over_union(a4, b4))
+    v = yu.intersection_over_union_numpy(a[0], b[0])
+    assert isinstance(v, np.ndarray) and v.shape == (1,) and v[0] == O.intersection_over_union(a[0], b[0])[0]
+    # unaligned view (offset by one float)
+    buf = _cuda(np.concatenate([[0], a[:64].ravel()]).astype(F32), dev)[1:].reshape(64, 4)
+    assert np.array_equal(yu.intersection_over_union(buf, _cuda(b[:64], dev)).cpu().numpy(),
+                          O.intersection_over_union(a[:64], b[:64]))
+    assert yu.intersection_over_union(torch.zeros((0, 4), device=dev), torch.zeros((0, 4), device=dev)).shape == (0, 1)
+
+
+# ---------------------------------------------------------------------------- decode
+@pytest.mark.parametrize("S,B,C,n", [(7, 2, 20, 64), (7, 2, 3, 5), (14, 3, 80, 6), (4, 1, 2, 9), (13, 5, 7, 3)])
+def test_decode_bit_exact(dev, S, B, C, n):
+    from yolohot import utils as yu
+    p = F.synth_dense(n, S, B, C, seed=S * 100 + C)
+    p[..., :C] = np.round(p[..., :C] * 8) / 8          # ties in the class argmax -> first max
+    got = yu.decode_predictions(_cuda(p, dev), C, B)
+    assert np.array_equal(got.cpu().numpy(), O.decode_predictions(p, C, B))
+    assert np.array_equal(yu.decode_predictions_numpy(p, C, B), O.decode_predictions(p, C, B))
+
+
+# ------------------------------------------------------------------ fused decode + NMS
+CASES = [
+    ("dense-voc", F.synth_dense, 64, 7, 2, 20, 0.5, 0.4),
+    ("dense-voc-odd-tail", F.synth_dense, 203, 7, 2, 20, 0.5, 0.4),
+    ("sparse-voc", F.synth_sparse, 256, 7, 2, 20, 0.5, 0.4),
+    ("ties-voc", F.synth_quantised, 128, 7, 2, 20, 0.5, 0.3),
+    ("ties-lowthr", F.synth_quantised, 64, 7, 2, 20, 0.2, 0.0),
+    ("stress", F.synth_stress, 12, 14, 3, 80, 0.5, 0.05),
+    ("stress-ties", F.synth_quantised, 10, 14, 3, 80, 0.5, 0.05),
+    ("tiny-grid", F.synth_dense, 33, 4, 1, 3, 0.3, 0.2),
+    ("s5-b3", F.synth_dense, 40, 5, 3, 11, 0.4, 0.5),
+    ("s9", F.synth_quantised, 20, 9, 2, 6, 0.5, 0.3),
+    ("s11-c1", F.synth_dense, 16, 11, 2, 1, 0.3, 0.3),
+    ("s16", F.synth_quantised, 5, 16, 2, 4, 0.5, 0.2),
+]
+
+
+@pytest.mark.parametrize("name,gen,n,S,B,C,it,ct", CASES, ids=[c[0] for c in CASES])
+def test_decode_nms_bit_exact(dev, name, gen, n, S, B, C, it, ct):
+    from yolohot import utils as yu
+    p = gen(n, S, B, C)
+    want = O.decode_nms(p, C, B, it, ct) if n * S * S <= 4000 else cport.decode_nms(p, C, B, it, ct)
+    got = yu.decode_nms(_cuda(p, dev), C, B, it, ct, return_index=True)
+    _check_nms(got, want, name)
+
+
+def test_decode_nms_paths_agree(dev, monkeypatch):
+    """TMA ring vs direct kernel, and an 8-byte (not 16) aligned input that must take the direct path."""
+    from yolohot import utils as yu
+    p = F.synth_dense(1000, seed=21)
+    want = cport.decode_nms(p, 20, 2)
+    _check_nms(yu.decode_nms(_cuda(p, dev), 20, 2, return_index=True), want, "tma")
+    monkeypatch.setenv("YH_TMA", "0")
+    _check_nms(yu.decode_nms(_cuda(p, dev), 20, 2, return_index=True), want, "direct")
+    monkeypatch.delenv("YH_TMA")
+    flat = _cuda(np.concatenate([np.zeros(2, F32), p.ravel()]), dev)[2:].reshape(p.shape)
+    assert flat.data_ptr() % 16 == 8
+    _check_nms(yu.decode_nms(flat, 20, 2, return_index=True), want, "8B-aligned")
+    for T, W, ST in ((4, 8, 2), (16, 16, 2), (8, 8, 5)):
+        monkeypatch.setenv("YH_TMA_T", str(T)); monkeypatch.setenv("YH_TMA_W", str(W)); monkeypatch.setenv("YH_TMA_STAGES", str(ST))
+        _check_nms(yu.decode_nms(_cuda(p, dev), 20, 2, return_index=True), want, f"tma T{T} W{W} ST{ST}")
+
+
+def test_decode_nms_edge_cases(dev):
+    from yolohot import utils as yu
+    # empty batch, nothing passes, everything passes with one class and identical boxes, single image
+    b, c = yu.decode_nms(torch.zeros((0, 7, 7, 30), device=dev), 20, 2)
+    assert b.shape == (0, 49, 6) and c.shape == (0,)
+    z = np.zeros((3, 7, 7, 30), F32)
+    _check_nms(yu.decode_nms(_cuda(z, dev), 20, 2, return_index=True), O.decode_nms(z, 20, 2), "zeros")
+    one = np.zeros((2, 7, 7, 30), F32)
+    one[..., 0] = 1; one[..., 20] = 0.9; one[..., 21:25] = [0.5, 0.5, 0.2, 0.2]
+    _check_nms(yu.decode_nms(_cuda(one, dev), 20, 2, return_index=True), O.decode_nms(one, 20, 2), "all-equal")
+    same_center = np.zeros((1, 7, 7, 30), F32)
+    same_center[..., 3] = 1; same_center[..., 20] = np.linspace(0.41, 0.99, 49).reshape(7, 7)
+    same_center[..., 23:25] = 0.3
+    _check_nms(yu.decode_nms(_cuda(same_center, dev), 20, 2, return_index=True), O.decode_nms(same_center, 20, 2), "chain")
+    yt, yp = F.utils_demo()
+    for y in (yt, yp):
+        _check_nms(yu.decode_nms(_cuda(y, dev), 3, 2, return_index=True), O.decode_nms(y, 3, 2), "utils-demo")
+    with pytest.raises(ValueError):
+        yu.decode_nms(torch.zeros((1, 7, 6, 30), device=dev), 20, 2)
+    with pytest.raises(NotImplementedError):
+        yu.decode_nms(torch.zeros((1, 17, 17, 30), device=dev), 20, 2)
+
+
+def test_reference_fixtures_through_reference_surface(dev):
+    """utils.py:757-769 and dataset.py:153 as the reference's own smoke blocks drive them."""
+    from yolohot import utils as yu
+    yt, yp = F.utils_demo()
+    nms = yu.non_max_suppression(yu.decode_predictions(_cuda(yp, dev), 3, 2)[0])
+    assert np.array_equal(nms.cpu().numpy(), G["utils_demo_nms_pred"])
+    nms_np = yu.non_max_suppression_numpy(yu.decode_predictions_numpy(yp, 3, 2)[0])
+    assert isinstance(nms_np, np.ndarray) and np.array_equal(nms_np, G["utils_demo_nms_pred"])
+    ev = yu.MeanAveragePrecision(3, 2)
+    ev.update_state(_cuda(yt, dev), _cuda(yp, dev))
+    assert abs(float(ev.result()) - float(G["utils_demo_map"])) <= 1e-6
+    assert np.array_equal(ev.all_pred_boxes_variable.cpu().numpy()[:, 1:], G["utils_demo_nms_pred"])
+    assert np.array_equal(ev.all_true_boxes_variable.cpu().numpy()[:, 1:], G["utils_demo_nms_true"])
+    lab = O.encode_labels(F.TEST_TXT_BOXES, 7, 3, 2)[None].astype(F32)
+    out = yu.non_max_suppression(yu.decode_predictions(_cuda(lab, dev), 3, 2)[0])
+    assert np.array_equal(out.cpu().numpy(), G["test_txt_nms"])
+    got = yu.decode_nms(_cuda(F.synth_dense(8, seed=1234), dev), 20, 2, return_index=True)
+    _check_nms(got, (G["dense8_boxes"], G["dense8_count"], G["dense8_idx"]), "golden dense8")
+
+
+def test_nms_rows_entry(dev):
+    """non_max_suppression on already decoded rows, incl. float class values the fused path never sees."""
+    from yolohot import utils as yu
+    rng = np.random.default_rng(4)
+    for M in (1, 31, 49, 100, 196, 256):
+        rows = rng.random((6, M, 6), dtype=F32)
+        rows[..., 0] = rng.integers(0, 4, (6, M)) * 0.5 - 0.5            # classes -0.5, 0, 0.5, 1.0
+        rows[..., 1] = np.round(rows[..., 1] * 16) / 16
+        rows[..., 4:6] = 0.2 + 0.4 * rows[..., 4:6]
+        outs = yu.non_max_suppression(_cuda(rows, dev), 0.4, 0.3)
+        for i in range(6):
+            assert np.array_equal(outs[i].cpu().numpy(), O.non_max_suppression(rows[i], 0.4, 0.3)), (M, i)
+    assert yu.non_max_suppression(_cuda(rows[0], dev), 0.5, 2.0).shape == (0, 6)
+    assert yu.non_max_suppression_2(_cuda(rows[0], dev)).shape[1] == 6
+
+
+def test_decode_nms_host_entry(dev):
+    """yh_decode_nms_host: NumPy in / NumPy out through the pipelined host path (several chunks)."""
+    from yolohot import utils as yu
+    p = F.synth_dense(40000, seed=8)
+    want = cport.decode_nms(p, 20, 2, nthreads=cport.num_threads())
+    got = yu.decode_nms(p, 20, 2, return_index=True)
+    assert all(isinstance(x, np.ndarray) for x in got)
+    _check_nms(got, want, "host")
+    pin = torch.from_numpy(p[:5001]).pin_memory().numpy()
+    _check_nms(yu.decode_nms(pin, 20, 2, return_index=True), tuple(w[:5001] for w in want), "host-pinned")
+
+
+def test_decode_nms_large_vs_cport_and_properties(dev):
+    """100k images against the C port; size-independent properties on the same output."""
+    from yolohot import utils as yu
+    torch.manual_seed(5)
+    p = torch.rand((100_000, 7, 7, 30), device=dev)
+    boxes, cnt, kidx = yu.decode_nms(p, 20, 2, return_index=True)
+    want = cport.decode_nms(p.cpu().numpy(), 20, 2, nthreads=cport.num_threads())
+    _check_nms((boxes, cnt, kidx), want, "100k")
+    m = torch.arange(49, device=dev)[None, :] < cnt[:, None]
+    conf = torch.where(m, boxes[..., 1], torch.full_like(boxes[..., 1], float("inf")))
+    assert bool((conf > 0.4).all())                                   # strict filter
+    c2 = torch.where(m, boxes[..., 1], torch.zeros_like(boxes[..., 1]))
+    assert bool((c2[:, 1:] <= c2[:, :-1]).all())                      # pick order = descending confidence
+    # idempotence: NMS of the kept rows keeps them all, in the same order
+    b2 = torch.where(m[..., None], boxes, torch.zeros_like(boxes))[:2000]
+    again = yu.non_max_suppression(b2)
+    for i in range(0, 2000, 97):
+        assert torch.equal(again[i], b2[i, :int(cnt[i])])
+
+
+# ------------------------------------------------------------------------------- loss
+@pytest.mark.parametrize("n,S,B,C", [(64, 7, 2, 20), (5, 7, 2, 3), (9, 14, 3, 80), (33, 4, 1, 2)])
+def test_loss_forward_backward(dev, n, S, B, C):
+    from yolohot import loss as yl
+    yt = F.synth_labels(n, S, B, C, seed=7)
+    yp = F.synth_loss_pred(yt.shape, seed=7)
+    ref = O.yolo_v1_loss(yt, yp, C, B)
+    fn = yl.YoloV1Loss(C, B)
+    p = _cuda(yp, dev).requires_grad_(True)
+    total = fn(_cuda(yt, dev), p)
+    assert total.dim() == 0 and fn.batch_size == n
+    terms = fn.last_terms.cpu().numpy()
+    for i, k in enumerate(("xy", "wh", "obj", "noobj", "cls", "total")):
+        assert abs(terms[i] - ref[k + "_f64"]) <= 1e-5 * max(abs(ref[k + "_f64"]), 1e-6), (k, terms[i], ref[k + "_f64"])
+    (2.0 * total).backward()                                   # upstream gradient is honoured
+    g = p.grad.cpu().numpy() / 2.0
+    g_ref = O.yolo_v1_loss_grad(yt, yp, C, B)
+    scale = np.abs(g_ref).max()
+    assert np.abs(g - g_ref).max() <= 1e-5 * scale + 1e-6, np.abs(g - g_ref).max()
+    assert np.array_equal(g == 0, g_ref == 0) or np.abs(g[g_ref == 0]).max() < 1e-6
+    # forward only (no grad requested) gives the same scalar; numpy in -> numpy scalar out
+    assert float(fn(_cuda(yt, dev), _cuda(yp, dev))) == float(total)
+    assert isinstance(fn(yt, yp), np.float32)
+
+
+def test_loss_reference_fixture_and_run_to_run(dev):
+    from yolohot import loss as yl
+    yt, yp = F.loss_demo()
+    fn = yl.YoloV1Loss(num_classes=3, num_boxes=2)
+    v = float(fn(_cuda(yt, dev), _cuda(yp, dev)))
+    assert abs(v - 0.17571506) <= 1e-5 * 0.17571506
+    terms, grad = yl.yolo_v1_loss_terms(_cuda(yt, dev), _cuda(yp, dev), 3, 2, grad=True)
+    np.testing.assert_allclose(terms.cpu().numpy(), G["loss_demo_terms"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(grad.cpu().numpy(), G["loss_demo_grad"], rtol=1e-4, atol=1e-6)
+    yt = F.synth_labels(512, seed=3)
+    yp = F.synth_loss_pred(yt.shape, seed=3)
+    a = yl.yolo_v1_loss_terms(_cuda(yt, dev), _cuda(yp, dev))
+    b = yl.yolo_v1_loss_terms(_cuda(yt, dev), _cuda(yp, dev))
+    assert torch.equal(a, b)                                           # deterministic reduction
+
+
+def test_loss_linearity_property(dev):
+    """Batch sum: loss(concat(a, b)) == loss(a) + loss(b) (loss.py:172-213 sums over everything)."""
+    from yolohot import loss as yl
+    yt = F.synth_labels(300, seed=13)
+    yp = F.synth_loss_pred(yt.shape, seed=13)
+    whole = yl.yolo_v1_loss_terms(_cuda(yt, dev), _cuda(yp, dev)).double().cpu().numpy()
+    parts = sum(yl.yolo_v1_loss_terms(_cuda(yt[lo:hi], dev), _cuda(yp[lo:hi], dev)).double().cpu().numpy()
+                for lo, hi in ((0, 77), (77, 300)))
+    np.testing.assert_allclose(whole, parts, rtol=2e-6)
+
+
+# -------------------------------------------------------------------------------- mAP
+def test_map_function_vs_oracle(dev):
+    from yolohot import utils as yu
+    yt = F.synth_labels(300, seed=11)
+    mp = F.synth_map_pred(yt)
+    oe = O.MeanAveragePrecision(20, 2)
+    oe.update_state(yt, mp)
+    t_rows, p_rows = oe.all_true_boxes_variable, oe.all_pred_boxes_variable
+    want, want_ap, _ = O.mean_average_precision(t_rows, p_rows, 20, return_details=True)
+    got, ap = yu.mean_average_precision(_cuda(t_rows, dev), _cuda(p_rows, dev), 20, return_ap=True)
+    assert abs(float(got) - float(want)) <= 1e-6
+    np.testing.assert_allclose(ap.cpu().numpy(), want_ap, atol=1e-6)
+    # row order of the inputs is arbitrary in the reference's contract: shuffle images (stable inside an image)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(300)
+    t2 = np.concatenate([t_rows[t_rows[:, 0] == i] for i in perm])
+    p2 = np.concatenate([p_rows[p_rows[:, 0] == i] for i in perm])
+    want2 = O.mean_average_precision(t2, p2, 20)
+    assert abs(float(yu.mean_average_precision(_cuda(t2, dev), _cuda(p2, dev), 20)) - float(want2)) <= 1e-6
+    # other thresholds, numpy twin, empty detections, class with no GT
+    for thr in (0.3, 0.75):
+        assert abs(float(yu.mean_average_precision_numpy(t_rows, p_rows, 20, thr)) -
+                   float(O.mean_average_precision(t_rows, p_rows, 20, thr))) <= 1e-6
+    assert float(yu.mean_average_precision(_cuda(t_rows, dev), torch.zeros((0, 7), device=dev), 20)) == 0.0
+    assert abs(float(yu.mean_average_precision_2(_cuda(t_rows, dev), _cuda(p_rows, dev), num_classes=25)) -
+               float(O.mean_average_precision(t_rows, p_rows, 25))) <= 1e-6
+
+
+def test_map_ties_and_duplicates(dev):
+    """Equal confidences (stable order) and several detections on one GT (only the first is TP)."""
+    from yolohot import utils as yu
+    rng = np.random.default_rng(3)
+    t_rows, p_rows = [], []
+    for img in range(60):
+        for _ in range(rng.integers(1, 4)):
+            c = rng.integers(0, 3)
+            box = [rng.random(), rng.random(), 0.2 + 0.3 * rng.random(), 0.2 + 0.3 * rng.random()]
+            t_rows.append([img, c, 1.0] + box)
+            for _ in range(rng.integers(0, 4)):
+                j = 0.02 * rng.standard_normal(4)
+                p_rows.append([img, c if rng.random() < 0.8 else (c + 1) % 3, rng.integers(1, 5) / 5.0] + list(np.array(box) + j))
+    t_rows, p_rows = np.array(t_rows, F32), np.array(p_rows, F32)
+    want = O.mean_average_precision(t_rows, p_rows, 3)
+    got = yu.mean_average_precision(_cuda(t_rows, dev), _cuda(p_rows, dev), 3)
+    assert abs(float(got) - float(want)) <= 1e-6 and 0.1 < float(want) < 1.0
+
+
+def test_evaluator_streaming_and_reset(dev):
+    from yolohot import metric as ym
+    from yolohot import utils as yu
+    yt = F.synth_labels(500, seed=11)
+    mp = F.synth_map_pred(yt)
+    oe = O.MeanAveragePrecision(20, 2)
+    oe.update_state(yt, mp)
+    ev = yu.MeanAveragePrecision(20, 2)
+    for lo in range(0, 500, 64):                                       # growing buffers, ragged last batch
+        ev.update_state(_cuda(yt[lo:lo + 64], dev), _cuda(mp[lo:lo + 64], dev))
+    assert ev.img_idx == 500
+    assert np.array_equal(ev.all_pred_boxes_variable.cpu().numpy(), oe.all_pred_boxes_variable)
+    assert np.array_equal(ev.all_true_boxes_variable.cpu().numpy(), oe.all_true_boxes_variable)
+    assert abs(float(ev.result()) - float(oe.result())) <= 1e-6
+    ev.reset_states()                                                  # utils.py:467-468 + :484-486
+    ev.update_state(_cuda(yt[:32], dev), _cuda(mp[:32], dev))
+    o2 = O.MeanAveragePrecision(20, 2)
+    o2.update_state(yt[:32], mp[:32])
+    assert np.array_equal(ev.all_pred_boxes_variable.cpu().numpy(), o2.all_pred_boxes_variable)
+    assert abs(float(ev.result()) - float(o2.result())) <= 1e-6
+    en = yu.MeanAveragePrecisionNumpy(20, 2)
+    en.update_state(yt[:32], mp[:32])
+    assert isinstance(en.all_pred_boxes_variable, np.ndarray) and abs(float(en.result()) - float(o2.result())) <= 1e-6
+    # stale metric.py evaluators: GT thresholded only (metric.py:81), driven as metric.py:142-155
+    mt, p1, p2 = F.metric_demo()
+    for cls in (ym.MeanAveragePrecision2, ym.MeanAveragePrecision):
+        e = cls()
+        for i in range(5):
+            e.update_state(_cuda(mt, dev), _cuda(p1 if i == 0 else p2, dev))
+        assert abs(float(e.result()) - float(G["metric_demo_map"])) <= 1e-6
+    o3 = O.MeanAveragePrecision(20, 2, nms_true=False)
+    o3.update_state(yt[:100], mp[:100])
+    e3 = ym.MeanAveragePrecision2()
+    e3.update_state(_cuda(yt[:100], dev), _cuda(mp[:100], dev))
+    assert np.array_equal(e3.all_true_bboxes_variable.cpu().numpy(), o3.all_true_boxes_variable)
+    assert abs(float(e3.result()) - float(o3.result())) <= 1e-6
+
+
+def test_sharded_map_single_process_emulation(dev):
+    """Ranks emulated as contiguous image shards on one GPU: per-shard yh_map_match, records
+    concatenated in shard order, yh_map_reduce == the unsharded value (multi-GPU parity rule)."""
+    from yolohot import utils as yu
+    yt = F.synth_labels(400, seed=11)
+    mp = F.synth_map_pred(yt)
+    ev = yu.MeanAveragePrecision(20, 2)
+    ev.update_state(_cuda(yt, dev), _cuda(mp, dev))
+    whole = float(ev.result())
+    ks, ts, gs = [], [], 0
+    for w in (3, 8):
+        ks, ts, gs = [], [], 0
+        for r in range(w):
+            lo, hi = 400 * r // w, 400 * (r + 1) // w
+            e = yu.MeanAveragePrecision(20, 2)
+            e.update_state(_cuda(yt[lo:hi], dev), _cuda(mp[lo:hi], dev))
+            k, t, g = yu.map_match(e.all_true_boxes_variable, e.all_pred_boxes_variable, 20, 0.5)
+            ks.append(k); ts.append(t); gs = gs + g
+        m, _ = yu.map_reduce(torch.cat(ks), torch.cat(ts), gs, 20)
+        assert float(m) == whole
