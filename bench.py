@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py - post-processing images/sec (decode + IoU + NMS) on B200, per BASELINE.json.
+
+  python bench.py --gpus N --steps K --warmup W            # own arm (libyolohot, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the reference's algorithm
+                                                            #   (oracle C port) on the host cores
+
+A step = one pass of the fused decode+IoU+NMS hot path (yh_decode_nms, utils.py:470-480 loop
+body) over BASELINE.json configs[1]: 1,000,000 synthetic YOLOv1 outputs (S=7, B=2, C=20, dense
+U[0,1), seed 2025) PER GPU (weak scaling, images sharded by contiguous range, no collective on
+this path).  `value` times the kernel with inputs resident in HBM (CUDA events on the launch
+stream, 5.88 GB per step >> L2); `e2e` times the same workload through the C-ABI host entry
+point yh_decode_nms_host with pinned HOST buffers (H2D + kernel + D2H inside the timed region).
+One JSON line on rank 0.  Nothing here reads /root/reference."""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "keras-object-detection_b200"))
+
+S, B, C = 7, 2, 20
+M, D = S * S, C + 5 * B
+IMG_IN = 4 * M * D            # 5,880 B read per image
+IMG_OUT_ROW = 24              # bytes written per kept row
+CONF_THR, IOU_THR = 0.4, 0.5  # utils.py:475
+METRIC = "post-processing images/sec (decode+IoU+NMS)"
+UNIT = "images/s"
+
+
+def env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("decode_nms_tma_kernel_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """NVML sampler of SM clock / throttle reasons during a timed region."""
+
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU implementation of the path = the oracle C port (the real one is TF
+    Python, not importable here), all host threads, bounded sample per step."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle import cport
+    cport.build()
+    cores = cport.num_threads()
+    n_step = env_int("YH_BENCH_REF_IMAGES", 262_144)
+    rng = np.random.Generator(np.random.PCG64(2025))
+    p = rng.random((n_step, S, S, D), dtype=np.float32)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cport.decode_nms(p[: n_step // 4], C, B, IOU_THR, CONF_THR, nthreads=cores, want_idx=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cport.decode_nms(p, C, B, IOU_THR, CONF_THR, nthreads=cores, want_idx=False)
+    dt = time.perf_counter() - t0
+    value = n_step * args.steps / dt
+    sample = f"{n_step} images/step x {args.steps} steps of the cfg2 workload (dense U[0,1), seed 2025), {cores} host threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: YOLOv1 S=7 B=2 C=20 decode+IoU+NMS (bounded sample of the 1M-image batch)",
+                   "images_per_step": n_step, "conf_threshold": CONF_THR, "iou_threshold": IOU_THR},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is TF-eager Python (not importable: no TensorFlow); this arm times oracle/yolo_oracle_c.c, "
+                "a C restatement of the same algorithm, which is far faster than the real reference would be",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------ own arm
+def run_own(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from yolohot import _lib
+    from yolohot import utils as yu
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    n_img = env_int("YH_BENCH_IMAGES", 1_000_000)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2025 + rank)
+    pred = torch.rand((n_img, S, S, D), generator=gen, device=dev, dtype=torch.float32)
+    boxes = torch.empty((n_img, M, 6), device=dev, dtype=torch.float32)
+    cnt = torch.empty((n_img,), device=dev, dtype=torch.int32)
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    def step():
+        _lib.check(L.yh_decode_nms(pred.data_ptr(), n_img, S, B, C, IOU_THR, CONF_THR, boxes.data_ptr(), cnt.data_ptr(),
+                                   None, sp), "yh_decode_nms")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    kept = int(cnt.sum().item())
+
+    # ---- timed region: K steps, one event pair per step (= per launch of the dominant kernel)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        barrier()
+        t_all0 = torch.cuda.Event(enable_timing=True)
+        t_all1 = torch.cuda.Event(enable_timing=True)
+        t_all0.record(stream)
+        for a, b in ev:
+            a.record(stream)
+            step()
+            b.record(stream)
+        t_all1.record(stream)
+        barrier()
+    launches = _lib.launch_count() - l0
+    total_ms = t_all0.elapsed_time(t_all1)
+    per_launch_ms = [a.elapsed_time(b) for a, b in ev]
+    ms_step = total_ms / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step, float(launches), float(kept)], device=dev, dtype=torch.float64)
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_step = float(mx[0])
+        launches_job = int(sm[1])
+    else:
+        launches_job = launches
+    value = world * n_img / (ms_step / 1000.0)
+
+    # ---- roofline of the dominant kernel (this rank's launches)
+    peak, peak_src = measured_peak()
+    algo_bytes = n_img * (IMG_IN + 4) + IMG_OUT_ROW * kept          # 4*S^2*D read + 24K + 4 written
+    k_ms = statistics.mean(per_launch_ms)
+    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "kernel": "decode_nms_tma_kernel<2,20,2>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_mean": k_ms, "kernel_ms_min": min(per_launch_ms),
+                "kept_rows_per_image": kept / n_img}
+
+    # ---- end to end through the C-ABI with pinned host buffers
+    e2e_n = env_int("YH_BENCH_E2E_IMAGES", n_img)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        while e2e_n > 65_536 and world * e2e_n * (IMG_IN + M * 24 + 4) * 2 > avail:
+            e2e_n //= 2
+    except Exception:
+        pass
+    h_in = torch.empty((e2e_n, S, S, D), dtype=torch.float32, pin_memory=True)
+    h_boxes = torch.empty((e2e_n, M, 6), dtype=torch.float32, pin_memory=True)
+    h_cnt = torch.empty((e2e_n,), dtype=torch.int32, pin_memory=True)
+    h_in.copy_(pred[:e2e_n])
+    torch.cuda.synchronize(dev)
+
+    def e2e_step():
+        _lib.check(L.yh_decode_nms_host(h_in.data_ptr(), e2e_n, S, B, C, IOU_THR, CONF_THR, h_boxes.data_ptr(),
+                                        h_cnt.data_ptr(), None, local), "yh_decode_nms_host")
+
+    e2e_step()
+    e2e_steps = max(2, min(args.steps, env_int("YH_BENCH_E2E_STEPS", 5)))
+    with ClockSampler(local) as clk2:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    ok_e2e = bool(torch.equal(h_cnt, cnt[:e2e_n].cpu()))
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e = {"value": world * e2e_n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e_n * IMG_IN,
+           "d2h_bytes_per_step": e2e_n * (M * 24 + 4), "images_per_step_per_gpu": e2e_n, "steps": e2e_steps,
+           "ms_per_step": 1000.0 * e2e_s, "api": "yh_decode_nms_host (C-ABI, pinned host buffers in/out)",
+           "counts_match_device_path": ok_e2e}
+    del h_in, h_boxes
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle C port on a bounded slice of the same inputs
+    cpu_baseline = None
+    extras = {}
+    if rank == 0 and world == 1:
+        from oracle import cport
+        cport.build()
+        cores = cport.num_threads()
+        n_cpu = env_int("YH_BENCH_CPU_IMAGES", 262_144)
+        sl = pred[:n_cpu].cpu().numpy()
+        cport.decode_nms(sl[:4096], C, B, IOU_THR, CONF_THR, nthreads=cores, want_idx=False)
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            _, c_cpu, _ = cport.decode_nms(sl, C, B, IOU_THR, CONF_THR, nthreads=cores, want_idx=False)
+            reps += 1
+            if time.perf_counter() - t0 > 10.0 or reps >= 40:
+                break
+        dt = time.perf_counter() - t0
+        audit = bool(np.array_equal(c_cpu, cnt[:n_cpu].cpu().numpy()))
+        cpu_baseline = {"value": n_cpu * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"first {n_cpu} images of the same batch x {reps} passes ({dt:.1f} s), oracle C port "
+                                  f"(reference itself is TF-eager Python, not importable: no TensorFlow)",
+                        "kept_counts_equal_gpu": audit}
+        # ---- the other BASELINE configs, briefly (kernel time, resident inputs)
+        extras = other_configs(torch, dev, L, _lib, yu, sp)
+
+    clocks = clk.summary()
+    clocks["e2e"] = clk2.summary()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "cfg2: YOLOv1 S=7 B=2 C=20 decode+IoU+NMS, 1M synthetic images per GPU, dense U[0,1) seed 2025",
+                   "images_per_gpu": n_img, "S": S, "B": B, "C": C, "conf_threshold": CONF_THR, "iou_threshold": IOU_THR,
+                   "sharding": f"images by contiguous range x{world}, no data-path collective",
+                   "l2": "inputs larger than L2 (5.88 GB read per step per GPU; no flush needed)"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_job, "clocks": clocks,
+    }
+    line.update(extras)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def other_configs(torch, dev, L, _lib, yu, sp):
+    """cfg2-sparse, cfg3 (loss fwd+bwd, batch 4096) and cfg4 (mAP, 5k images) - context numbers."""
+    import numpy as np
+    from tests import fixtures as F
+    out = {}
+    peak, _ = measured_peak()
+
+    def timed(fn, reps, flush=None):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            if flush is not None:
+                flush.add_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return statistics.mean(ts), min(ts)
+
+    # cfg2 sparse: confidences u^32, ~2.7 candidates per image
+    n = env_int("YH_BENCH_IMAGES", 1_000_000)
+    gen = torch.Generator(device=dev); gen.manual_seed(2025)
+    p = torch.rand((n, S, S, D), generator=gen, device=dev)
+    for b in range(B):
+        p[..., C + 5 * b] = p[..., C + 5 * b] ** 32
+        p[..., C + 5 * b + 3:C + 5 * b + 5] = 0.05 + 0.45 * p[..., C + 5 * b + 3:C + 5 * b + 5]
+    boxes = torch.empty((n, M, 6), device=dev); cnt = torch.empty((n,), device=dev, dtype=torch.int32)
+    f = lambda: _lib.check(L.yh_decode_nms(p.data_ptr(), n, S, B, C, IOU_THR, CONF_THR, boxes.data_ptr(), cnt.data_ptr(), None, sp))
+    ms, mn = timed(f, 10)
+    kept = int(cnt.sum().item())
+    gbs = (n * (IMG_IN + 4) + 24 * kept) / (ms * 1e-3) / 1e9
+    out["cfg2_sparse"] = {"images_per_s": n / (ms * 1e-3), "ms": ms, "GBps": gbs, "frac_hbm": gbs / peak, "kept_per_image": kept / n}
+    del p, boxes, cnt
+    # cfg3: loss fwd+bwd batch 4096 (72 MB working set < L2 -> flush L2 between iterations)
+    yt = torch.from_numpy(F.synth_labels(4096, seed=7)).to(dev)
+    yp = torch.from_numpy(F.synth_loss_pred(tuple(yt.shape), seed=7)).to(dev)
+    terms = torch.empty(6, device=dev); grad = torch.empty_like(yp)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)      # 256 MB > 126 MB L2
+    f = lambda: _lib.check(L.yh_loss(yt.data_ptr(), yp.data_ptr(), 4096 * M, B, C, 5.0, 0.5, terms.data_ptr(), grad.data_ptr(), sp))
+    ms, mn = timed(f, 20, flush)
+    gbs = 3 * 4096 * IMG_IN / (ms * 1e-3) / 1e9
+    out["cfg3_loss_fwd_bwd_b4096"] = {"ms": ms, "ms_min": mn, "GBps": gbs, "frac_hbm": gbs / peak, "loss": float(terms[5]),
+                                      "l2": "flushed (256 MB write) before every iteration"}
+    # cfg4: mAP over 5k images, single GPU (evaluator update + result)
+    yt5 = F.synth_labels(5000, seed=11); mp5 = F.synth_map_pred(yt5)
+    a, b_ = torch.from_numpy(yt5).to(dev), torch.from_numpy(mp5).to(dev)
+    def run_map():
+        e = yu.MeanAveragePrecision(C, B)
+        e.update_state(a, b_)
+        return e.result()
+    for _ in range(2):
+        m = run_map()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        m = run_map()
+    mval = float(m)
+    out["cfg4_map_5k_images"] = {"ms_update_plus_result": (time.perf_counter() - t0) / 5 * 1e3, "mAP": mval}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_own(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

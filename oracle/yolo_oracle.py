@@ -307,7 +307,7 @@ def yolo_v1_loss(y_true, y_pred, num_classes=20, num_boxes=2,
 
 
 def yolo_v1_loss_grad(y_true, y_pred, num_classes=20, num_boxes=2,
-                      lambda_coord=5.0, lambda_noobj=0.5):
+                      lambda_coord=5.0, lambda_noobj=0.5, float32_forward=True):
     """Closed-form d(loss)/d(y_pred), evaluated in float64 from the
     float32 inputs, with TF's sub-gradient conventions: clip passes gradient on
     [0, 1] inclusive; max/min route ties to their FIRST argument (the true box,
@@ -330,13 +330,28 @@ def yolo_v1_loss_grad(y_true, y_pred, num_classes=20, num_boxes=2,
         return p[(*idx, base + off)]
     c = take(0); px = take(1); py = take(2); pw = take(3); ph = take(4)
     tx, ty, tw, th = t[..., C + 1], t[..., C + 2], t[..., C + 3], t[..., C + 4]
-    # forward IoU pieces in float64
-    x1n, x1x = (tx - tw) / 2, (tx + tw) / 2
-    y1n, y1x = (ty - th) / 2, (ty + th) / 2
-    x2n, x2x = (px - pw) / 2, (px + pw) / 2
-    y2n, y2x = (py - ph) / 2, (py + ph) / 2
-    dx = np.minimum(x1x, x2x) - np.maximum(x1n, x2n)
-    dy = np.minimum(y1x, y2x) - np.maximum(y1n, y2n)
+    # forward IoU pieces: corners and extents are taken from the FLOAT32 forward (utils.py:24-39),
+    # because TF's autodiff decides ties of max/min/clip on the float32 values it computed
+    # (the loss.py:219-234 fixture sits exactly on such a tie: (0.49-0.09)/2 == (0.5-0.1)/2 in
+    # float32 but not in float64); the smooth factors are then evaluated in float64.
+    two = F32(2.0)
+    def take32(off):
+        return p32[(*idx, base + off)]
+    px32, py32, pw32, ph32 = take32(1), take32(2), take32(3), take32(4)
+    tx32, ty32, tw32, th32 = t32[..., C + 1], t32[..., C + 2], t32[..., C + 3], t32[..., C + 4]
+    x1n, x1x = ((tx32 - tw32) / two).astype(np.float64), ((tx32 + tw32) / two).astype(np.float64)
+    y1n, y1x = ((ty32 - th32) / two).astype(np.float64), ((ty32 + th32) / two).astype(np.float64)
+    x2n, x2x = ((px32 - pw32) / two).astype(np.float64), ((px32 + pw32) / two).astype(np.float64)
+    y2n, y2x = ((py32 - ph32) / two).astype(np.float64), ((py32 + ph32) / two).astype(np.float64)
+    dx = (np.minimum(x1x, x2x).astype(F32) - np.maximum(x1n, x2n).astype(F32)).astype(np.float64)
+    dy = (np.minimum(y1x, y2x).astype(F32) - np.maximum(y1n, y2n).astype(F32)).astype(np.float64)
+    if not float32_forward:   # pure float64 evaluation (cross-check against float64 autograd)
+        x1n, x1x = (tx - tw) / 2, (tx + tw) / 2
+        y1n, y1x = (ty - th) / 2, (ty + th) / 2
+        x2n, x2x = (px - pw) / 2, (px + pw) / 2
+        y2n, y2x = (py - ph) / 2, (py + ph) / 2
+        dx = np.minimum(x1x, x2x) - np.maximum(x1n, x2n)
+        dy = np.minimum(y1x, y2x) - np.maximum(y1n, y2n)
     cw, ch = np.clip(dx, 0, 1), np.clip(dy, 0, 1)
     inter = cw * ch
     a1 = np.abs((x1x - x1n) * (y1x - y1n))

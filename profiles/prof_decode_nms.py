@@ -1,0 +1,41 @@
+"""Short driver for ncu: a few launches of the fused decode+NMS kernel on the cfg2 workload
+(1M dense images unless YH_PROF_IMAGES is set).  `python profiles/prof_decode_nms.py [dense|sparse|stress]`."""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "keras-object-detection_b200"))
+import torch  # noqa: E402
+
+from yolohot import _lib  # noqa: E402
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "dense"
+n = int(os.environ.get("YH_PROF_IMAGES", 1_000_000))
+S, B, C, thr = 7, 2, 20, 0.4
+if mode == "stress":
+    S, B, C, thr = 14, 3, 80, 0.05
+    n = int(os.environ.get("YH_PROF_IMAGES", 65_536))
+D = C + 5 * B
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev)
+g.manual_seed(2025)
+p = torch.rand((n, S, S, D), generator=g, device=dev)
+if mode == "sparse":
+    for b in range(B):
+        p[..., C + 5 * b] = p[..., C + 5 * b] ** 32
+boxes = torch.empty((n, S * S, 6), device=dev)
+cnt = torch.empty((n,), device=dev, dtype=torch.int32)
+L = _lib.lib()
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+reps = int(os.environ.get("YH_PROF_REPS", 5))
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+ev[0].record()
+for i in range(reps):
+    _lib.check(L.yh_decode_nms(p.data_ptr(), n, S, B, C, 0.5, thr, boxes.data_ptr(), cnt.data_ptr(), None, st))
+    ev[i + 1].record()
+torch.cuda.synchronize()
+ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
+kept = int(cnt.sum())
+print(f"{mode}: n={n} S={S} B={B} C={C} ms={['%.3f' % m for m in ms]} kept/img={kept / n:.2f} "
+      f"GB/s(best)={(n * (4 * S * S * D + 4) + 24 * kept) / min(ms) / 1e6:.0f}")
