@@ -35,39 +35,56 @@ struct NmsCfg {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// per-warp workspace carve-up (MP = 32 * NS slots)
+// per-warp workspace carve-up (MP = 32 * NS slots).  Only what other lanes must see lives in
+// shared memory: the compact confidences for the rank loop, and per RANK POSITION the box
+// corners / area / class key for the IoU tests and the output slot.  Confidence, box and class
+// of a cell stay in the registers of the lane that decoded it.
 template <int NS, bool kFloatCls>
 struct WarpWs {
     static constexpr int MP = 32 * NS;
-    float4 *sbox;     // [MP]  boxes in rank order
-    float *sconf;     // [MP]
-    int *smeta;       // [MP]  (class key << 8) | source index
-    float *ckey;      // [MP + 4] compact candidate confidences (source order), -inf padded
+    float4 *scor;     // [MP]  corners (xmin, xmax, ymin, ymax) of the box at rank position q  (utils.py:24-32)
+    float *sarea;     // [MP]  |area| of that box                                               (utils.py:40-41)
+    int *smeta;       // [MP]  class key of rank position q (scratch for the duplicate-rank test before)
+    float *ckey;      // [MP + 4] compact candidate confidences (source order), -inf padded;
+    int *outpos;      //          aliased afterwards: output slot of rank position q, -1 = suppressed
     float *cclsf;     // [MP]  compact float classes          (kFloatCls only)
-    float *sclsf;     // [MP]  float classes in rank order    (kFloatCls only)
     unsigned *tbl;    // [tbl_rows * NS] class key -> lanes holding that class, per slot
 
     __host__ __device__ static int bytes(int tbl_rows)
     {
         int b = MP * 16 + MP * 4 + MP * 4 + (MP + 4) * 4;
-        if (kFloatCls) b += MP * 8;
+        if (kFloatCls) b += MP * 4;
         b += tbl_rows * NS * 4;
         return (b + 15) & ~15;
     }
     __device__ explicit WarpWs(unsigned char *p)
     {
-        sbox = reinterpret_cast<float4 *>(p);  p += MP * 16;
-        sconf = reinterpret_cast<float *>(p);  p += MP * 4;
+        scor = reinterpret_cast<float4 *>(p);  p += MP * 16;
+        sarea = reinterpret_cast<float *>(p);  p += MP * 4;
         smeta = reinterpret_cast<int *>(p);    p += MP * 4;
-        ckey = reinterpret_cast<float *>(p);   p += (MP + 4) * 4;
-        cclsf = sclsf = nullptr;
+        ckey = reinterpret_cast<float *>(p);
+        outpos = reinterpret_cast<int *>(p);   p += (MP + 4) * 4;
+        cclsf = nullptr;
         if (kFloatCls) {
             cclsf = reinterpret_cast<float *>(p);  p += MP * 4;
-            sclsf = reinterpret_cast<float *>(p);  p += MP * 4;
         }
         tbl = reinterpret_cast<unsigned *>(p);
     }
 };
+
+// IoU test of the reference from precomputed corners/areas: p = chosen (earlier) box, q = later
+// box.  Same float32 operations in the same order as utils.py:34-43 (min/max/+ commute bit for
+// bit), so the decision is the reference's.  A zero intersection gives IoU = +0 exactly
+// (denominator >= 1e-6 > 0): skip the IEEE division, whose zero-numerator case is a slow path.
+__device__ __forceinline__ bool suppresses(const float4 &pc, float pa, const float4 &qc, float qa, float iou_thr)
+{
+    const float iw = clip01(__fsub_rn(fminf(pc.y, qc.y), fmaxf(pc.x, qc.x)));
+    const float ih = clip01(__fsub_rn(fminf(pc.w, qc.w), fmaxf(pc.z, qc.z)));
+    const float inter = __fmul_rn(iw, ih);
+    float v = 0.0f;
+    if (inter != 0.0f) v = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(pa, qa), inter), 1e-6f));
+    return !(v < iou_thr);                                   // utils.py:108 keeps iff iou < thr
+}
 
 // ------------------------------------------------------------------------------------------
 // Phases B..F for one image held in registers: slot t of this lane is source index
@@ -101,11 +118,13 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
     if (lane < 4) ws.ckey[n + lane] = -INFINITY;   // pad to a multiple of 4 for the float4 loop
     __syncwarp();
 
-    // ---- B: stable descending rank (utils.py:98) ----
+    // ---- B: stable descending rank (utils.py:98): r = #{j : s_j > s}; counted in float
+    //      (exact below 2^24) so that each comparison is one FSET + one FADD ----
     int r[NS];
-#pragma unroll
-    for (int t = 0; t < NS; ++t) r[t] = 0;
     {
+        float rf[NS];
+#pragma unroll
+        for (int t = 0; t < NS; ++t) rf[t] = 0.0f;
         const float4 *k4p = reinterpret_cast<const float4 *>(ws.ckey);
         const int n4 = (n + 3) >> 2;
         for (int g = 0; g < n4; ++g) {
@@ -113,9 +132,14 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
 #pragma unroll
             for (int t = 0; t < NS; ++t) {
                 const float c = conf[t];
-                r[t] += (k.x > c) + (k.y > c) + (k.z > c) + (k.w > c);
+                rf[t] += (k.x > c) ? 1.0f : 0.0f;
+                rf[t] += (k.y > c) ? 1.0f : 0.0f;
+                rf[t] += (k.z > c) ? 1.0f : 0.0f;
+                rf[t] += (k.w > c) ? 1.0f : 0.0f;
             }
         }
+#pragma unroll
+        for (int t = 0; t < NS; ++t) r[t] = static_cast<int>(rf[t]);
     }
     // a duplicate rank <=> equal confidences exist: only then pay for the tie-break pass
     {
@@ -128,7 +152,6 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
         for (int t = 0; t < NS; ++t)
             if (pass[t]) dup |= (ws.smeta[r[t]] != ci[t]);
         dup = __any_sync(FULL, dup);
-        __syncwarp();
         if (dup) {
             for (int j = 0; j < n; ++j) {
                 const float k = ws.ckey[j];
@@ -149,15 +172,17 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
                 if (pass[t] && f == __int_as_float(cls[t])) key[t] = j;
         }
     }
-    // scatter to rank order
+    __syncwarp();   // every lane is done with smeta (scratch) and ckey before they are rewritten
+    // scatter corners / area / class key to rank order                              (utils.py:24-32,40)
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         if (pass[t]) {
             const int q = r[t];
-            ws.sbox[q] = box[t];
-            ws.sconf[q] = conf[t];
-            ws.smeta[q] = (key[t] << 8) | (lane + 32 * t);
-            if (kFloatCls) ws.sclsf[q] = __int_as_float(cls[t]);
+            const float xn = __fmul_rn(__fsub_rn(box[t].x, box[t].z), 0.5f), xx = __fmul_rn(__fadd_rn(box[t].x, box[t].z), 0.5f);
+            const float yn = __fmul_rn(__fsub_rn(box[t].y, box[t].w), 0.5f), yx = __fmul_rn(__fadd_rn(box[t].y, box[t].w), 0.5f);
+            ws.scor[q] = make_float4(xn, xx, yn, yx);
+            ws.sarea[q] = fabsf(__fmul_rn(__fsub_rn(xx, xn), __fsub_rn(yx, yn)));
+            ws.smeta[q] = key[t];
         }
     }
     __syncwarp();
@@ -165,22 +190,17 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
     // ---- C: same-class masks.  Slot t of this lane now is rank position q = lane + 32 t ----
     const int NT = (n + 31) >> 5;
     bool act[NS];
-    int meta[NS];
-    float4 mb[NS];
+    int qkey[NS];
     unsigned lead = 0;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         const int q = lane + 32 * t;
         act[t] = q < n;
-        meta[t] = 0;
-        if (act[t]) {
-            meta[t] = ws.smeta[q];
-            mb[t] = ws.sbox[q];
-        }
+        qkey[t] = act[t] ? ws.smeta[q] : 0;
         if (t < NT) {
-            const unsigned m = __match_any_sync(FULL, act[t] ? (meta[t] >> 8) : (0x7f000000 + lane));
+            const unsigned m = __match_any_sync(FULL, act[t] ? qkey[t] : (0x7f000000 + lane));
             if (act[t] && (__ffs(m) - 1) == lane) {
-                ws.tbl[(meta[t] >> 8) * NS + t] = m;
+                ws.tbl[qkey[t] * NS + t] = m;
                 lead |= 1u << t;
             }
         }
@@ -197,7 +217,9 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         if (t < NT && act[t]) {
-            const unsigned *row = ws.tbl + (meta[t] >> 8) * NS;
+            const unsigned *row = ws.tbl + qkey[t] * NS;
+            const float4 qc = ws.scor[lane + 32 * t];
+            const float qa = ws.sarea[lane + 32 * t];
 #pragma unroll
             for (int t2 = 0; t2 <= t; ++t2) {
                 unsigned w = row[t2];
@@ -205,9 +227,7 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
                 while (w) {
                     const int b = __ffs(w) - 1;
                     w &= w - 1;
-                    const float4 pb = ws.sbox[32 * t2 + b];
-                    const float v = iou_ref(pb, mb[t]);            // (chosen, later) as utils.py:108
-                    if (!(v < cfg.iou_thr)) supp[t][t2] |= 1u << b;
+                    if (suppresses(ws.scor[32 * t2 + b], ws.sarea[32 * t2 + b], qc, qa, cfg.iou_thr)) supp[t][t2] |= 1u << b;
                 }
             }
         }
@@ -215,7 +235,7 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
     __syncwarp();
 #pragma unroll
     for (int t = 0; t < NS; ++t)
-        if (lead & (1u << t)) ws.tbl[(meta[t] >> 8) * NS + t] = 0u;   // leave the table zeroed
+        if (lead & (1u << t)) ws.tbl[qkey[t] * NS + t] = 0u;   // leave the table zeroed
 
     // ---- E: greedy keep flags, fixed point of keep[q] = !any(supp[q] & keep) ----
     bool alive[NS];
@@ -240,21 +260,28 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
         if (!__any_sync(FULL, ch)) break;
     }
 
-    // ---- F: kept rows in pick order (utils.py:112) ----
+    // ---- F: output slot of every rank position, then each cell's lane writes its own row in
+    //      pick order (utils.py:112) from the registers it decoded into ----
     int K = 0;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
-        if (alive[t]) {
-            const int q = lane + 32 * t;
-            const int pos = K + __popc(kw[t] & lt_mask);
-            const float c = kFloatCls ? ws.sclsf[q] : static_cast<float>(meta[t] >> 8);   // utils.py:175
-            float2 *o = reinterpret_cast<float2 *>(out_rows + 6 * pos);
-            o[0] = make_float2(c, ws.sconf[q]);
-            o[1] = make_float2(mb[t].x, mb[t].y);
-            o[2] = make_float2(mb[t].z, mb[t].w);
-            if (out_idx) out_idx[pos] = meta[t] & 255;
-        }
+        if (act[t]) ws.outpos[lane + 32 * t] = alive[t] ? K + __popc(kw[t] & lt_mask) : -1;
         K += __popc(kw[t]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        if (pass[t]) {
+            const int pos = ws.outpos[r[t]];
+            if (pos >= 0) {
+                const float c = kFloatCls ? __int_as_float(cls[t]) : static_cast<float>(cls[t]);   // utils.py:175
+                float2 *o = reinterpret_cast<float2 *>(out_rows + 6 * pos);
+                o[0] = make_float2(c, conf[t]);
+                o[1] = make_float2(box[t].x, box[t].y);
+                o[2] = make_float2(box[t].z, box[t].w);
+                if (out_idx) out_idx[pos] = lane + 32 * t;
+            }
+        }
     }
     __syncwarp();   // workspace is reused by the next image
     return K;
@@ -368,7 +395,7 @@ struct TmaCfg {
 };
 
 template <int NS, int CT, int BT>
-__global__ void __launch_bounds__(544, 1) decode_nms_tma_kernel(const float *__restrict__ pred, NmsCfg cfg, TmaCfg tc,
+__global__ void __launch_bounds__(800, 1) decode_nms_tma_kernel(const float *__restrict__ pred, NmsCfg cfg, TmaCfg tc,
                                                                 float *__restrict__ out_boxes,
                                                                 int *__restrict__ out_count, int *__restrict__ out_idx)
 {
@@ -396,14 +423,15 @@ __global__ void __launch_bounds__(544, 1) decode_nms_tma_kernel(const float *__r
         if (lane == 0) {
             const uint64_t pol = l2_evict_first_policy();
             const unsigned char *src = reinterpret_cast<const unsigned char *>(pred);
+            int s = 0;
+            uint32_t ph = 0;
             for (int64_t it = 0; it < my_tiles; ++it) {
-                const int s = static_cast<int>(it % tc.ST);
-                const uint32_t ph = static_cast<uint32_t>((it / tc.ST) & 1);
                 mbar_wait(empty + s, ph ^ 1u);
                 const int64_t tile = blockIdx.x + it * gridDim.x;
                 mbar_arrive_expect_tx(full + s, tc.tile_bytes);
                 bulk_g2s(tiles + static_cast<size_t>(s) * tc.tile_bytes, src + tile * tc.tile_bytes, tc.tile_bytes,
                          full + s, pol);
+                if (++s == tc.ST) { s = 0; ph ^= 1u; }
             }
         }
         return;
@@ -426,9 +454,9 @@ __global__ void __launch_bounds__(544, 1) decode_nms_tma_kernel(const float *__r
         colf[t] = static_cast<float>(cell % cfg.S);
     }
     const int img_floats = cfg.M * cfg.D;
+    int s = g % tc.ST;                                   // stage / phase of tile `it`, kept incrementally
+    uint32_t ph = static_cast<uint32_t>((g / tc.ST) & 1);
     for (int64_t it = g; it < my_tiles; it += G) {
-        const int s = static_cast<int>(it % tc.ST);
-        const uint32_t ph = static_cast<uint32_t>((it / tc.ST) & 1);
         mbar_wait(full + s, ph);
         const float *base = reinterpret_cast<const float *>(tiles + static_cast<size_t>(s) * tc.tile_bytes) + j * img_floats;
         float conf[NS];
@@ -445,6 +473,8 @@ __global__ void __launch_bounds__(544, 1) decode_nms_tma_kernel(const float *__r
         const int K = nms_warp<NS, false>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
                                           out_idx ? out_idx + img * cfg.M : nullptr);
         if (lane == 0) out_count[img] = K;
+        s += G;
+        while (s >= tc.ST) { s -= tc.ST; ph ^= 1u; }
     }
 }
 
@@ -594,17 +624,29 @@ static int launch_fused(const float *pred, int64_t n, NmsCfg cfg, float *out_box
     const bool tma_on = env_int("YH_TMA", 1) != 0;
     if (tma_on && (reinterpret_cast<uintptr_t>(pred) % 16 == 0) && img_bytes <= 12 * 1024) {
         TmaCfg tc;
-        tc.W = env_int("YH_TMA_W", 16);
+        tc.W = env_int("YH_TMA_W", 24);
         tc.T = env_int("YH_TMA_T", 8);
-        if (tc.W < 1 || tc.W > 16) tc.W = 16;
+        if (tc.W < 1 || tc.W > 24) tc.W = 24;
+        if (tc.T < 1) tc.T = 8;
         while (tc.T > 1 && ((tc.W % tc.T) != 0 || tc.T * img_bytes > 64 * 1024)) tc.T >>= 1;
-        if ((tc.T * img_bytes) % 16 == 0 && n >= tc.T) {
+        if ((tc.W % tc.T) == 0 && (tc.T * img_bytes) % 16 == 0 && n >= tc.T) {
             tc.tile_bytes = static_cast<uint32_t>(tc.T * img_bytes);
             cfg.ws_bytes = WarpWs<NS, false>::bytes(cfg.tbl_rows);
-            const size_t fixed = 2 * 8 * 8 /*barriers*/ + 16 + static_cast<size_t>(tc.W) * cfg.ws_bytes + 128;
-            int stages = env_int("YH_TMA_STAGES", 4);
-            while (stages > 1 && fixed + static_cast<size_t>(stages) * tc.tile_bytes > 227 * 1024) --stages;
-            tc.ST = std::min(stages, 8);
+            // Every stage must always be consumed by the same warp group, so that a group's waits on
+            // a stage's mbarrier are strictly sequential (parity waits are only unambiguous one
+            // phase apart): the stage count is a multiple of the group count G = W / T.
+            int G = tc.W / tc.T;
+            size_t fixed = 2 * 8 * 8 /*barriers*/ + 16 + static_cast<size_t>(tc.W) * cfg.ws_bytes + 128;
+            int cap = std::min(8, env_int("YH_TMA_STAGES", 8));
+            auto fit = [&](size_t fx) { return fx >= 227 * 1024 ? 0 : static_cast<int>((227 * 1024 - fx) / tc.tile_bytes); };
+            int stages = (std::min(cap, fit(fixed)) / G) * G;
+            if (stages < G || stages < 2) {             // not enough room: one group only
+                tc.W = tc.T;
+                G = 1;
+                fixed = 2 * 8 * 8 + 16 + static_cast<size_t>(tc.W) * cfg.ws_bytes + 128;
+                stages = std::min(cap, fit(fixed));
+            }
+            tc.ST = stages;
             tc.n_tiles = n / tc.T;
             const size_t smem = fixed + static_cast<size_t>(tc.ST) * tc.tile_bytes;
             if (tc.ST >= 2 && smem <= 227 * 1024) {
