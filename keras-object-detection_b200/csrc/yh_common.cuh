@@ -119,6 +119,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// same, for a waiter that is not latency critical (the TMA producer runs stages ahead): sleep
+// between polls so its spin does not take issue slots from the consumer warps of its SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, unsigned ns)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 // global -> shared bulk copy; completion is signalled on `bar` as `bytes` of transaction count.
 // dst/src 16-byte aligned, bytes a multiple of 16.  SASS: UBLKCP.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,

@@ -100,16 +100,17 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
     const unsigned lt_mask = (1u << lane) - 1u;
 
     // ---- A': compaction of the survivors (utils.py:95, strict >) ----
-    bool pass[NS];
+    unsigned pass_m = 0u;                          // bit t: this lane's slot t survives the filter
     int ci[NS];
     int n = 0;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
-        pass[t] = valid[t] && (conf[t] > cfg.conf_thr);
-        const unsigned b = __ballot_sync(FULL, pass[t]);
+        const bool ps = valid[t] && (conf[t] > cfg.conf_thr);
+        pass_m |= ps ? (1u << t) : 0u;
+        const unsigned b = __ballot_sync(FULL, ps);
         ci[t] = n + __popc(b & lt_mask);
         n += __popc(b);
-        if (pass[t]) {
+        if (ps) {
             ws.ckey[ci[t]] = conf[t];
             if (kFloatCls) ws.cclsf[ci[t]] = __int_as_float(cls[t]);
         }
@@ -145,18 +146,18 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
     {
 #pragma unroll
         for (int t = 0; t < NS; ++t)
-            if (pass[t]) ws.smeta[r[t]] = ci[t];
+            if (((pass_m >> t) & 1u)) ws.smeta[r[t]] = ci[t];
         __syncwarp();
         bool dup = false;
 #pragma unroll
         for (int t = 0; t < NS; ++t)
-            if (pass[t]) dup |= (ws.smeta[r[t]] != ci[t]);
+            if (((pass_m >> t) & 1u)) dup |= (ws.smeta[r[t]] != ci[t]);
         dup = __any_sync(FULL, dup);
         if (dup) {
             for (int j = 0; j < n; ++j) {
                 const float k = ws.ckey[j];
 #pragma unroll
-                for (int t = 0; t < NS; ++t) r[t] += (pass[t] && j < ci[t] && k == conf[t]) ? 1 : 0;
+                for (int t = 0; t < NS; ++t) r[t] += (((pass_m >> t) & 1u) && j < ci[t] && k == conf[t]) ? 1 : 0;
             }
         }
     }
@@ -169,14 +170,14 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
             const float f = ws.cclsf[j];
 #pragma unroll
             for (int t = 0; t < NS; ++t)
-                if (pass[t] && f == __int_as_float(cls[t])) key[t] = j;
+                if (((pass_m >> t) & 1u) && f == __int_as_float(cls[t])) key[t] = j;
         }
     }
     __syncwarp();   // every lane is done with smeta (scratch) and ckey before they are rewritten
     // scatter corners / area / class key to rank order                              (utils.py:24-32,40)
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
-        if (pass[t]) {
+        if (((pass_m >> t) & 1u)) {
             const int q = r[t];
             const float xn = __fmul_rn(__fsub_rn(box[t].x, box[t].z), 0.5f), xx = __fmul_rn(__fadd_rn(box[t].x, box[t].z), 0.5f);
             const float yn = __fmul_rn(__fsub_rn(box[t].y, box[t].w), 0.5f), yx = __fmul_rn(__fadd_rn(box[t].y, box[t].w), 0.5f);
@@ -189,17 +190,18 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
 
     // ---- C: same-class masks.  Slot t of this lane now is rank position q = lane + 32 t ----
     const int NT = (n + 31) >> 5;
-    bool act[NS];
+    unsigned act_m = 0u;                           // bit t: rank position lane + 32 t exists
     int qkey[NS];
     unsigned lead = 0;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         const int q = lane + 32 * t;
-        act[t] = q < n;
-        qkey[t] = act[t] ? ws.smeta[q] : 0;
+        const bool ac = q < n;
+        act_m |= ac ? (1u << t) : 0u;
+        qkey[t] = ac ? ws.smeta[q] : 0;
         if (t < NT) {
-            const unsigned m = __match_any_sync(FULL, act[t] ? qkey[t] : (0x7f000000 + lane));
-            if (act[t] && (__ffs(m) - 1) == lane) {
+            const unsigned m = __match_any_sync(FULL, ac ? qkey[t] : (0x7f000000 + lane));
+            if (ac && (__ffs(m) - 1) == lane) {
                 ws.tbl[qkey[t] * NS + t] = m;
                 lead |= 1u << t;
             }
@@ -214,20 +216,65 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
 #pragma unroll
         for (int t2 = 0; t2 < NS; ++t2) supp[t][t2] = 0u;
     }
+    if constexpr (NS == 2) {
+        // One loop per lane over ALL its predecessor bits (slot-1 candidate first, then slot 0), so
+        // the warp runs max_lane(total) trips instead of the sum of three per-word maxima.
+        unsigned w0 = 0u, cur_lo = 0u, cur_hi = 0u;
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), qc = c0;
+        float a0 = 0.f, qa = 0.f;
+        unsigned pending0 = 0u, on1 = 0u;
+        if ((act_m & 1u)) {
+            w0 = ws.tbl[qkey[0] * 2] & lt_mask;
+            c0 = ws.scor[lane];
+            a0 = ws.sarea[lane];
+        }
+        if ((act_m & 2u)) {
+            cur_lo = ws.tbl[qkey[1] * 2];
+            cur_hi = ws.tbl[qkey[1] * 2 + 1] & lt_mask;
+        }
+        if (cur_lo | cur_hi) {
+            qc = ws.scor[lane + 32];
+            qa = ws.sarea[lane + 32];
+            pending0 = (w0 != 0u) ? 1u : 0u;
+            on1 = 1u;
+        } else {
+            cur_lo = w0;
+            qc = c0;
+            qa = a0;
+        }
+        unsigned s_lo = 0u, s_hi = 0u;
+        for (;;) {
+            if ((cur_lo | cur_hi) == 0u) {
+                if (!pending0) break;
+                supp[1][0] = s_lo; supp[1][1] = s_hi;      // slot-1 candidate done, switch to slot 0
+                s_lo = s_hi = 0u;
+                cur_lo = w0; qc = c0; qa = a0;
+                pending0 = 0u; on1 = 0u;
+            }
+            const bool lo = cur_lo != 0u;
+            const unsigned w = lo ? cur_lo : cur_hi;
+            const unsigned bit = w & (0u - w);
+            const int p = (31 - __clz(bit)) + (lo ? 0 : 32);
+            const unsigned sb = suppresses(ws.scor[p], ws.sarea[p], qc, qa, cfg.iou_thr) ? bit : 0u;
+            if (lo) { cur_lo ^= bit; s_lo |= sb; } else { cur_hi ^= bit; s_hi |= sb; }
+        }
+        if (on1) { supp[1][0] = s_lo; supp[1][1] = s_hi; } else { supp[0][0] = s_lo; }
+    } else {
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
-        if (t < NT && act[t]) {
-            const unsigned *row = ws.tbl + qkey[t] * NS;
-            const float4 qc = ws.scor[lane + 32 * t];
-            const float qa = ws.sarea[lane + 32 * t];
+        for (int t = 0; t < NS; ++t) {
+            if (t < NT && ((act_m >> t) & 1u)) {
+                const unsigned *row = ws.tbl + qkey[t] * NS;
+                const float4 qc = ws.scor[lane + 32 * t];
+                const float qa = ws.sarea[lane + 32 * t];
 #pragma unroll
-            for (int t2 = 0; t2 <= t; ++t2) {
-                unsigned w = row[t2];
-                if (t2 == t) w &= lt_mask;
-                while (w) {
-                    const int b = __ffs(w) - 1;
-                    w &= w - 1;
-                    if (suppresses(ws.scor[32 * t2 + b], ws.sarea[32 * t2 + b], qc, qa, cfg.iou_thr)) supp[t][t2] |= 1u << b;
+                for (int t2 = 0; t2 <= t; ++t2) {
+                    unsigned w = row[t2];
+                    if (t2 == t) w &= lt_mask;
+                    while (w) {
+                        const int b = __ffs(w) - 1;
+                        w &= w - 1;
+                        if (suppresses(ws.scor[32 * t2 + b], ws.sarea[32 * t2 + b], qc, qa, cfg.iou_thr)) supp[t][t2] |= 1u << b;
+                    }
                 }
             }
         }
@@ -238,40 +285,36 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
         if (lead & (1u << t)) ws.tbl[qkey[t] * NS + t] = 0u;   // leave the table zeroed
 
     // ---- E: greedy keep flags, fixed point of keep[q] = !any(supp[q] & keep) ----
-    bool alive[NS];
+    unsigned alive_m = act_m;                                  // bit t: rank position lane + 32 t is kept
     unsigned kw[NS];
-#pragma unroll
-    for (int t = 0; t < NS; ++t) alive[t] = act[t];
     for (;;) {
 #pragma unroll
-        for (int t = 0; t < NS; ++t) kw[t] = (t < NT) ? __ballot_sync(FULL, alive[t]) : 0u;
-        bool ch = false;
+        for (int t = 0; t < NS; ++t) kw[t] = (t < NT) ? __ballot_sync(FULL, (alive_m >> t) & 1u) : 0u;
+        unsigned nm = 0u;
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
-            if (act[t]) {
-                unsigned s = 0u;
+            unsigned sgot = 0u;
 #pragma unroll
-                for (int t2 = 0; t2 <= t; ++t2) s |= supp[t][t2] & kw[t2];
-                const bool nv = (s == 0u);
-                ch |= (nv != alive[t]);
-                alive[t] = nv;
-            }
+            for (int t2 = 0; t2 <= t; ++t2) sgot |= supp[t][t2] & kw[t2];
+            nm |= (sgot == 0u) ? (1u << t) : 0u;
         }
+        nm &= act_m;
+        const bool ch = nm != alive_m;
+        alive_m = nm;
         if (!__any_sync(FULL, ch)) break;
     }
-
     // ---- F: output slot of every rank position, then each cell's lane writes its own row in
     //      pick order (utils.py:112) from the registers it decoded into ----
     int K = 0;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
-        if (act[t]) ws.outpos[lane + 32 * t] = alive[t] ? K + __popc(kw[t] & lt_mask) : -1;
+        if (((act_m >> t) & 1u)) ws.outpos[lane + 32 * t] = ((alive_m >> t) & 1u) ? K + __popc(kw[t] & lt_mask) : -1;
         K += __popc(kw[t]);
     }
     __syncwarp();
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
-        if (pass[t]) {
+        if (((pass_m >> t) & 1u)) {
             const int pos = ws.outpos[r[t]];
             if (pos >= 0) {
                 const float c = kFloatCls ? __int_as_float(cls[t]) : static_cast<float>(cls[t]);   // utils.py:175
@@ -426,7 +469,7 @@ __global__ void __launch_bounds__(800, 1) decode_nms_tma_kernel(const float *__r
             int s = 0;
             uint32_t ph = 0;
             for (int64_t it = 0; it < my_tiles; ++it) {
-                mbar_wait(empty + s, ph ^ 1u);
+                mbar_wait_relaxed(empty + s, ph ^ 1u, 256);
                 const int64_t tile = blockIdx.x + it * gridDim.x;
                 mbar_arrive_expect_tx(full + s, tc.tile_bytes);
                 bulk_g2s(tiles + static_cast<size_t>(s) * tc.tile_bytes, src + tile * tc.tile_bytes, tc.tile_bytes,

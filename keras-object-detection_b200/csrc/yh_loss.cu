@@ -1,4 +1,4 @@
-// yh_loss.cu - K5: YoloV1Loss forward + hand-written backward in one pass.  sm_100a.
+// yh_loss.cu - K5: YoloV1Loss forward + hand-written backward in one launch.  sm_100a.
 //
 // Replaces loss.py:120-215 (YoloV1Loss.call) and the TF autodiff backward of it:
 //   IoU(true box, each pred box) loss.py:126-133, first-max responsible box :136, the five
@@ -10,6 +10,7 @@
 // loss.py:189); TF sub-gradient conventions: clip passes on [0,1] inclusive, max/min send
 // ties to their first argument (the true box), sign(0) = 0.
 #include <algorithm>
+#include <mutex>
 
 #include "yh_common.cuh"
 
@@ -19,8 +20,10 @@ struct LossCfg {
     int B, C, D;
     float lc, ln;           // lambda_coord, lambda_noobj
     int64_t n_cells;
-    int tile_cells;         // == blockDim.x
+    int tile_cells;         // cells per shared-memory tile
 };
+
+constexpr int kLossThreads = 128;
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -31,18 +34,28 @@ __device__ __forceinline__ double warp_sum(double v)
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
-// one tile = tile_cells consecutive cells; y_true / y_pred tiles staged in shared memory with
-// coalesced 128-bit loads, one thread per cell, gradient written back through the same tile.
+// One tile = tile_cells consecutive cells; y_true / y_pred tiles are staged in shared memory with
+// coalesced 128-bit streaming loads.  Box part: one thread per cell (IoU, responsible box, the four
+// box/confidence terms and their gradients).  Class part: one warp per cell, lanes over classes
+// (conflict-free shared-memory rows).  The gradient goes back through the y_pred tile with 128-bit
+// stores.  Sums: per-thread float64 -> warp -> block partials; the last block to finish (ticket
+// counter) adds the partials of all blocks in index order and writes the six outputs, so there is a
+// single launch and the result does not depend on which block came last.
 template <bool kGrad>
-__global__ void __launch_bounds__(256) loss_kernel(const float *__restrict__ yt, const float *__restrict__ yp, LossCfg cfg,
-                                                   float *__restrict__ grad, double *__restrict__ partials)
+__global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
+                                                            LossCfg cfg, float *__restrict__ grad,
+                                                            double *__restrict__ partials, unsigned *__restrict__ ticket,
+                                                            float *__restrict__ out_terms)
 {
     extern __shared__ float4 smem4[];
     float *st = reinterpret_cast<float *>(smem4);
     float *sp = st + static_cast<size_t>(cfg.tile_cells) * cfg.D;
-    __shared__ double red[8][5];
+    __shared__ double red[kLossThreads / 32][5];
+    __shared__ double fin[5][26];
+    __shared__ bool is_last;
 
     const int C = cfg.C, B = cfg.B, D = cfg.D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int64_t n_tiles = (cfg.n_cells + cfg.tile_cells - 1) / cfg.tile_cells;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(yt) | reinterpret_cast<uintptr_t>(yp) |
                           (kGrad ? reinterpret_cast<uintptr_t>(grad) : 0)) % 16 == 0) &&
@@ -77,9 +90,10 @@ __global__ void __launch_bounds__(256) loss_kernel(const float *__restrict__ yt,
         }
         __syncthreads();
 
-        if (static_cast<int>(threadIdx.x) < cells) {
-            const float *t = st + threadIdx.x * D;
-            float *p = sp + threadIdx.x * D;
+        // ---- box part: thread per cell; touches only channels >= C of the y_pred tile ----
+        for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
+            const float *t = st + cell * D;
+            float *p = sp + cell * D;
             const float obj = t[C];                                           // loss.py:162
             const float tx = t[C + 1], ty = t[C + 2], tw = t[C + 3], th = t[C + 4];
             // responsible box: first max of IoU(true, pred_b)               // loss.py:126-137
@@ -93,33 +107,25 @@ __global__ void __launch_bounds__(256) loss_kernel(const float *__restrict__ yt,
             float *q = p + C + 5 * k;
             const float c = q[0], px = q[1], py = q[2], pw = q[3], ph = q[4];
             const float noobj = __fsub_rn(1.0f, obj);                         // loss.py:163
-            // ---- forward terms (float32 element-wise, as the reference) ----
-            const float dx = __fsub_rn(tx, px), dy = __fsub_rn(ty, py);
-            sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dx, dx)));    // loss.py:171
-            sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dy, dy)));
-            const float sw = sgn(pw), sh = sgn(ph);
-            const float rw = __fsqrt_rn(__fadd_rn(fabsf(pw), 1e-6f)), rh = __fsqrt_rn(__fadd_rn(fabsf(ph), 1e-6f));
-            const float dw = __fsub_rn(__fsqrt_rn(tw), __fmul_rn(sw, rw));    // loss.py:176-178
-            const float dh = __fsub_rn(__fsqrt_rn(th), __fmul_rn(sh, rh));
-            swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dw, dw)));
-            swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dh, dh)));
-            const float e = __fsub_rn(u, c);
-            sob += static_cast<double>(__fmul_rn(obj, __fmul_rn(e, e)));      // loss.py:189
             const float z = __fsub_rn(0.0f, c);
             snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));    // loss.py:197
+            float g_c = cfg.ln * 2.0f * noobj * c;
+            float g_x = 0.f, g_y = 0.f, g_w = 0.f, g_h = 0.f;
             if (obj != 0.0f) {
-                for (int j = 0; j < C; ++j) {                                  // loss.py:206
-                    const float d = __fsub_rn(t[j], p[j]);
-                    scl += static_cast<double>(__fmul_rn(obj, __fmul_rn(d, d)));
-                }
-            }
-            // ---- backward w.r.t. y_pred ----
-            if (kGrad) {
-                float g_c = cfg.ln * 2.0f * noobj * c;
-                float g_x = 0.f, g_y = 0.f, g_w = 0.f, g_h = 0.f;
-                if (obj != 0.0f) {
-                    for (int j = 0; j < C; ++j) p[j] = -2.0f * obj * (t[j] - p[j]);
-                    // IoU pieces again, with their partial derivatives
+                // forward terms (float32 element-wise, as the reference)
+                const float dx = __fsub_rn(tx, px), dy = __fsub_rn(ty, py);
+                sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dx, dx)));    // loss.py:171
+                sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dy, dy)));
+                const float sw = sgn(pw), sh = sgn(ph);
+                const float rw = __fsqrt_rn(__fadd_rn(fabsf(pw), 1e-6f)), rh = __fsqrt_rn(__fadd_rn(fabsf(ph), 1e-6f));
+                const float dw = __fsub_rn(__fsqrt_rn(tw), __fmul_rn(sw, rw));    // loss.py:176-178
+                const float dh = __fsub_rn(__fsqrt_rn(th), __fmul_rn(sh, rh));
+                swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dw, dw)));
+                swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dh, dh)));
+                const float e = __fsub_rn(u, c);
+                sob += static_cast<double>(__fmul_rn(obj, __fmul_rn(e, e)));      // loss.py:189
+                if (kGrad) {
+                    // IoU pieces again, with their partial derivatives (SURVEY.md App. A.6)
                     const float x1n = (tx - tw) * 0.5f, x1x = (tx + tw) * 0.5f;
                     const float y1n = (ty - th) * 0.5f, y1x = (ty + th) * 0.5f;
                     const float x2n = (px - pw) * 0.5f, x2x = (px + pw) * 0.5f;
@@ -150,11 +156,22 @@ __global__ void __launch_bounds__(256) loss_kernel(const float *__restrict__ yt,
                     g_y = -2.0f * cfg.lc * obj * dy + e2 * du_dpy;
                     g_w = -2.0f * cfg.lc * obj * dw * (sw * sw) / (2.0f * rw) + e2 * du_dpw;
                     g_h = -2.0f * cfg.lc * obj * dh * (sh * sh) / (2.0f * rh) + e2 * du_dph;
-                } else {
-                    for (int j = 0; j < C; ++j) p[j] = 0.f;
                 }
+            }
+            if (kGrad) {
                 for (int j = C; j < D; ++j) p[j] = 0.f;
                 q[0] = g_c; q[1] = g_x; q[2] = g_y; q[3] = g_w; q[4] = g_h;
+            }
+        }
+        // ---- class part: warp per cell, lanes over classes; touches only channels < C ----
+        for (int cell = warp; cell < cells; cell += nwarp) {
+            const float *t = st + cell * D;
+            float *p = sp + cell * D;
+            const float obj = t[C];
+            for (int j = lane; j < C; j += 32) {                              // loss.py:206
+                const float d = __fsub_rn(t[j], p[j]);
+                if (obj != 0.0f) scl += static_cast<double>(__fmul_rn(obj, __fmul_rn(d, d)));
+                if (kGrad) p[j] = (obj != 0.0f) ? -2.0f * obj * d : 0.0f;
             }
         }
         __syncthreads();
@@ -169,12 +186,11 @@ __global__ void __launch_bounds__(256) loss_kernel(const float *__restrict__ yt,
             } else {
                 for (int i = threadIdx.x; i < nfl; i += blockDim.x) gg[i] = sp[i];
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
 
     // stage 1 of the deterministic reduction: lanes -> warp -> block, fixed order
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     sxy = warp_sum(sxy); swh = warp_sum(swh); sob = warp_sum(sob); snb = warp_sum(snb); scl = warp_sum(scl);
     if (lane == 0) {
         red[warp][0] = sxy; red[warp][1] = swh; red[warp][2] = sob; red[warp][3] = snb; red[warp][4] = scl;
@@ -182,28 +198,58 @@ __global__ void __launch_bounds__(256) loss_kernel(const float *__restrict__ yt,
     __syncthreads();
     if (threadIdx.x < 5) {
         double s = 0;
-        const int nw = blockDim.x >> 5;
-        for (int w = 0; w < nw; ++w) s += red[w][threadIdx.x];
+        for (int w = 0; w < nwarp; ++w) s += red[w][threadIdx.x];
         partials[static_cast<size_t>(blockIdx.x) * 5 + threadIdx.x] = s;
+    }
+    // stage 2: the last block (ticket) sums all partials in block-index order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(ticket, 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // thread i: term i % 5, blocks (i / 5), (i / 5) + 25, ...; then 25 sub-sums per term in index order
+    const int term = threadIdx.x % 5, slot = threadIdx.x / 5;
+    if (slot < 25) {
+        double s = 0;
+        for (int b = slot; b < static_cast<int>(gridDim.x); b += 25) s += __ldcg(partials + static_cast<size_t>(b) * 5 + term);
+        fin[term][slot] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double tot = 0;
+        for (int i = 0; i < 25; ++i) tot += fin[threadIdx.x][i];
+        fin[threadIdx.x][25] = tot;
+        out_terms[threadIdx.x] = static_cast<float>(tot);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                                   // loss.py:210-213
+        out_terms[5] = static_cast<float>(static_cast<double>(cfg.lc) * (fin[0][25] + fin[1][25]) + fin[2][25] +
+                                          static_cast<double>(cfg.ln) * fin[3][25] + fin[4][25]);
+        *ticket = 0u;                                                         // ready for the next launch
     }
 }
 
-// stage 2: one warp, term `lane` (< 5) summed over blocks in index order
-__global__ void loss_finalize_kernel(const double *__restrict__ partials, int n_blocks, float lc, float ln,
-                                     float *__restrict__ out_terms)
-{
-    __shared__ double tot[5];
-    if (threadIdx.x < 5) {
-        double s = 0;
-        for (int b = 0; b < n_blocks; ++b) s += partials[static_cast<size_t>(b) * 5 + threadIdx.x];
-        tot[threadIdx.x] = s;
-        out_terms[threadIdx.x] = static_cast<float>(s);
-    }
-    __syncwarp();
-    if (threadIdx.x == 0)                                                       // loss.py:210-213
-        out_terms[5] = static_cast<float>(static_cast<double>(lc) * (tot[0] + tot[1]) + tot[2] +
-                                          static_cast<double>(ln) * tot[3] + tot[4]);
-}
+// Per-device scratch of the loss: block partials + ticket.  Calls on different streams are
+// ordered through an event so the scratch is never shared by two running launches.
+struct LossScratch {
+    double *partials = nullptr;
+    unsigned *ticket = nullptr;
+    int cap_blocks = 0;
+    cudaEvent_t ev = nullptr;
+    cudaStream_t last = nullptr;
+    bool used = false;
+};
+struct LossGeo {
+    size_t smem = 0;
+    int per_sm = 0;
+};
+static LossScratch g_loss[64];
+static LossGeo g_geo[2][64];
+static std::mutex g_loss_mu;
 
 }  // namespace yh
 
@@ -218,8 +264,8 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LossCfg cfg;
     cfg.B = B; cfg.C = C; cfg.D = C + 5 * B; cfg.lc = lambda_coord; cfg.ln = lambda_noobj; cfg.n_cells = n_cells;
-    int tile = 256;
-    while (tile > 32 && static_cast<size_t>(tile) * cfg.D * 8 > 96 * 1024) tile >>= 1;
+    int tile = 128;
+    while (tile > 32 && static_cast<size_t>(tile) * cfg.D * 8 > 100 * 1024) tile >>= 1;
     const size_t smem = static_cast<size_t>(tile) * cfg.D * 8;
     if (smem > 227 * 1024) {
         set_error("loss: C + 5B = %d too large for the shared-memory tile", cfg.D);
@@ -228,25 +274,42 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
     cfg.tile_cells = tile;
     const int64_t n_tiles = (n_cells + tile - 1) / tile;
     auto kern = out_grad ? loss_kernel<true> : loss_kernel<false>;
-    YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int per_sm = 1;
-    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tile, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * per_sm)));
-    double *partials = nullptr;
-    YH_CUDA(cudaMallocAsync(&partials, sizeof(double) * 5 * grid, st));
-    kern<<<grid, tile, smem, st>>>(y_true, y_pred, cfg, out_grad, partials);
-    {
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { cudaFreeAsync(partials, st); return cuda_fail(e, "loss_kernel"); }
-        count_launch();
+
+    int dev = 0;
+    YH_CUDA(cudaGetDevice(&dev));
+    YH_REQUIRE(dev >= 0 && dev < 64, "loss: device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_loss_mu);
+    // launch geometry is cached: the attribute / occupancy queries cost more than the kernel
+    LossGeo &g = g_geo[out_grad ? 1 : 0][dev];
+    if (g.smem != smem || g.per_sm == 0) {
+        YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int per_sm = 1;
+        YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLossThreads, smem));
+        g.smem = smem;
+        g.per_sm = per_sm < 1 ? 1 : per_sm;
     }
-    loss_finalize_kernel<<<1, 32, 0, st>>>(partials, grid, lambda_coord, lambda_noobj, out_terms);
-    {
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { cudaFreeAsync(partials, st); return cuda_fail(e, "loss_finalize_kernel"); }
-        count_launch();
+    const int grid = static_cast<int>(
+        std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * g.per_sm)));
+    LossScratch &sc = g_loss[dev];
+    if (sc.cap_blocks < grid) {
+        if (sc.partials) {
+            YH_CUDA(cudaDeviceSynchronize());
+            YH_CUDA(cudaFree(sc.partials));
+            YH_CUDA(cudaFree(sc.ticket));
+        }
+        const int cap = std::max(grid, sm_count() * 16);
+        YH_CUDA(cudaMalloc(&sc.partials, sizeof(double) * 5 * cap));
+        YH_CUDA(cudaMalloc(&sc.ticket, sizeof(unsigned)));
+        YH_CUDA(cudaMemset(sc.ticket, 0, sizeof(unsigned)));
+        YH_CUDA(cudaDeviceSynchronize());
+        sc.cap_blocks = cap;
+        if (!sc.ev) YH_CUDA(cudaEventCreateWithFlags(&sc.ev, cudaEventDisableTiming));
     }
-    YH_CUDA(cudaFreeAsync(partials, st));
+    if (sc.used && sc.last != st) YH_CUDA(cudaStreamWaitEvent(st, sc.ev, 0));
+    kern<<<grid, kLossThreads, smem, st>>>(y_true, y_pred, cfg, out_grad, sc.partials, sc.ticket, out_terms);
+    YH_LAUNCH_CHECK("loss_kernel");
+    YH_CUDA(cudaEventRecord(sc.ev, st));
+    sc.used = true;
+    sc.last = st;
     return YH_OK;
 }

@@ -219,6 +219,23 @@ struct AsyncBuf {   // stream-ordered scratch, freed on scope exit
     template <class T> T *as() { return static_cast<T *>(p); }
 };
 
+// The stream-ordered allocator trims its pool at every synchronisation unless a release threshold
+// is set; the evaluator synchronises often (result() returns a host scalar), so keep the scratch.
+static int keep_pool()
+{
+    static bool done[64] = {false};
+    int dev = 0;
+    YH_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+        cudaMemPool_t pool;
+        YH_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t thr = 1ull << 30;      // retain up to 1 GiB of freed scratch
+        YH_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        done[dev] = true;
+    }
+    return YH_OK;
+}
+
 static int bits_for(int C)
 {
     int b = 1;
@@ -238,6 +255,9 @@ extern "C" int yh_map_match(const float *true_rows, int64_t nt, const float *pre
     YH_REQUIRE(out_gt_per_class != nullptr, "map_match: out_gt_per_class is null");
     YH_REQUIRE((nt == 0 || true_rows) && (np == 0 || (pred_rows && out_keys && out_tp)), "map_match: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
+    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
+    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
     YH_CUDA(cudaMemsetAsync(out_gt_per_class, 0, sizeof(int32_t) * C, st));
     const int end_bit = bits_for(C);
 
@@ -287,6 +307,9 @@ extern "C" int yh_map_reduce(const uint64_t *keys, const uint8_t *tp, int64_t nr
     YH_REQUIRE(C >= 1 && nrec >= 0 && nrec < (1ll << 31), "map_reduce: bad sizes");
     YH_REQUIRE(gt_per_class && out_map && (nrec == 0 || (keys && tp)), "map_reduce: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
+    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
+    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
     const int end_bit = bits_for(C);
     AsyncBuf sk(st), stp(st), cum(st), start(st), ap(st), tmp(st);
     YH_CUDA(sk.alloc(8 * nrec)); YH_CUDA(stp.alloc(nrec)); YH_CUDA(cum.alloc(4 * nrec));
@@ -322,6 +345,9 @@ extern "C" int yh_rows_append(const float *boxes, const int32_t *count, int64_t 
     YH_REQUIRE(boxes && count && row_cursor && (out_capacity == 0 || out_rows), "rows_append: null pointer");
     YH_REQUIRE(n < (1ll << 31), "rows_append: too many images in one call");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
+    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
+    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
     AsyncBuf offs(st), tmp(st);
     YH_CUDA(offs.alloc(8 * n));
     size_t tb = 0;
