@@ -31,6 +31,7 @@ struct NmsCfg {
     float iou_thr, conf_thr;
     int ws_bytes;            // per-warp workspace bytes
     int tbl_rows;            // rows of the class table (C for fused, 32*NS for row input)
+    int stage_bytes;         // direct kernel: per-warp staging buffer for one slot (32 cells), 0 = none
 };
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -385,17 +386,48 @@ __device__ __forceinline__ void decode_cell(const float *__restrict__ p, const N
 }
 
 // ------------------------------------------------------------------------------------------
-// Direct kernel: one warp per image, cells read straight from global memory.
-// Any shape (S*S <= 32 NS), any alignment >= 4 B (8 B for the compile-time even-D path).
+// Direct kernel: one warp per image, no CTA-level cooperation.  Covers tails, inputs that are
+// only 8-byte aligned, and images too large for the TMA ring (e.g. S=14, B=3, C=80: 74 KB).
+// Slot t of an image (cells 32t .. 32t+31) is one contiguous chunk of 32*D floats: the warp copies it
+// into its own shared-memory staging buffer with coalesced vector loads, then every lane decodes its
+// cell from shared memory (row stride D words).  Reading the cells straight from global memory would
+// cost one L1 wavefront per lane per load (32 different lines per instruction).
+// Any shape (S*S <= 32 NS), any alignment >= 4 B.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy_to_smem(float *__restrict__ dst, const float *__restrict__ src, int nfl, int lane)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    if ((a & 15) == 0) {
+        const int n4 = nfl >> 2;
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+        int i = lane;
+#pragma unroll 4
+        for (; i < n4; i += 32) d4[i] = __ldcs(s4 + i);
+        for (int j = (n4 << 2) + lane; j < nfl; j += 32) dst[j] = __ldcs(src + j);
+    } else if ((a & 7) == 0) {
+        const int n2 = nfl >> 1;
+        const float2 *s2 = reinterpret_cast<const float2 *>(src);
+        float2 *d2 = reinterpret_cast<float2 *>(dst);
+#pragma unroll 4
+        for (int i = lane; i < n2; i += 32) d2[i] = __ldcs(s2 + i);
+        for (int j = (n2 << 1) + lane; j < nfl; j += 32) dst[j] = __ldcs(src + j);
+    } else {
+#pragma unroll 4
+        for (int j = lane; j < nfl; j += 32) dst[j] = __ldcs(src + j);
+    }
+}
+
 template <int NS, int CT, int BT>
-__global__ void __launch_bounds__(256) decode_nms_direct_kernel(const float *__restrict__ pred, int64_t n, NmsCfg cfg,
+__global__ void __launch_bounds__(512) decode_nms_direct_kernel(const float *__restrict__ pred, int64_t n, NmsCfg cfg,
                                                                 float *__restrict__ out_boxes,
                                                                 int *__restrict__ out_count, int *__restrict__ out_idx)
 {
     extern __shared__ uint4 smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    WarpWs<NS, false> ws(reinterpret_cast<unsigned char *>(smem_raw) + warp * cfg.ws_bytes);
+    unsigned char *mine = reinterpret_cast<unsigned char *>(smem_raw) + static_cast<size_t>(warp) * (cfg.ws_bytes + cfg.stage_bytes);
+    WarpWs<NS, false> ws(mine);
+    float *stage = reinterpret_cast<float *>(mine + cfg.ws_bytes);
     for (int i = lane; i < cfg.tbl_rows * NS; i += 32) ws.tbl[i] = 0u;
     __syncwarp();
 
@@ -417,7 +449,92 @@ __global__ void __launch_bounds__(256) decode_nms_direct_kernel(const float *__r
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
             conf[t] = -INFINITY; cls[t] = 0; box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid[t]) decode_cell<CT, BT>(base + (lane + 32 * t) * cfg.D, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
+            const int cells = min(32, cfg.M - 32 * t);
+            if (cells > 0) {
+                if (cfg.stage_bytes > 0) {
+                    __syncwarp();                                  // the previous slot has been consumed
+                    warp_copy_to_smem(stage, base + 32 * t * cfg.D, cells * cfg.D, lane);
+                    __syncwarp();
+                    if (valid[t]) decode_cell<0, 0>(stage + lane * cfg.D, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
+                } else if (valid[t]) {                             // straight from global / L1 (more resident warps)
+                    decode_cell<CT, BT>(base + (lane + 32 * t) * cfg.D, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
+                }
+            }
+        }
+        const int K = nms_warp<NS, false>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
+                                          out_idx ? out_idx + img * cfg.M : nullptr);
+        if (lane == 0) out_count[img] = K;
+    }
+}
+
+// Same work split, but every warp runs its own two-deep cp.async.bulk (TMA) pipeline over the flat
+// sequence of its (image, slot) chunks: chunk c lands in buffer c & 1 and completes mbarrier c & 1;
+// chunk c + 1 is issued as soon as chunk c - 1 has been decoded, so the first slot of the NEXT image
+// streams in while the NMS phases of the current one run.  Needs 16-byte aligned chunks.
+template <int NS, int CT, int BT>
+__global__ void __launch_bounds__(512) decode_nms_warp_tma_kernel(const float *__restrict__ pred, int64_t n, NmsCfg cfg,
+                                                                  float *__restrict__ out_boxes,
+                                                                  int *__restrict__ out_count, int *__restrict__ out_idx)
+{
+    extern __shared__ uint4 smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int per_warp = cfg.ws_bytes + 2 * cfg.stage_bytes + 16;
+    unsigned char *mine = reinterpret_cast<unsigned char *>(smem_raw) + static_cast<size_t>(warp) * per_warp;
+    WarpWs<NS, false> ws(mine);
+    unsigned char *stage = mine + cfg.ws_bytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(mine + cfg.ws_bytes + 2 * cfg.stage_bytes);
+    for (int i = lane; i < cfg.tbl_rows * NS; i += 32) ws.tbl[i] = 0u;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    float colf[NS], rowf[NS];
+    bool valid[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int cell = lane + 32 * t;
+        valid[t] = cell < cfg.M;
+        rowf[t] = static_cast<float>(cell / cfg.S);
+        colf[t] = static_cast<float>(cell % cfg.S);
+    }
+    const int slots = (cfg.M + 31) >> 5;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * wpb;
+    const int64_t img0 = static_cast<int64_t>(blockIdx.x) * wpb + warp;
+    const uint64_t pol = l2_evict_first_policy();
+    const uint32_t slot_bytes = 32u * cfg.D * 4u;
+
+    // chunk (image, t) -> issue into buffer `b`
+    auto issue = [&](int64_t img, int t, int b) {
+        const uint32_t bytes = static_cast<uint32_t>(min(32, cfg.M - 32 * t)) * cfg.D * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the buffer vs. the async write
+        mbar_arrive_expect_tx(bar + b, bytes);
+        bulk_g2s(stage + static_cast<size_t>(b) * cfg.stage_bytes,
+                 reinterpret_cast<const unsigned char *>(pred + img * cfg.M * cfg.D) + static_cast<size_t>(t) * slot_bytes, bytes,
+                 bar + b, pol);
+    };
+    if (img0 < n && lane == 0) issue(img0, 0, 0);
+    uint32_t c = 0;                                               // running chunk counter of this warp
+    for (int64_t img = img0; img < n; img += stride) {
+        float conf[NS];
+        float4 box[NS];
+        int cls[NS];
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            conf[t] = -INFINITY; cls[t] = 0; box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < slots) {
+                __syncwarp();                                      // chunk c - 1 (other buffer) has been consumed
+                if (lane == 0) {                                   // prefetch chunk c + 1 into the other buffer
+                    if (t + 1 < slots) issue(img, t + 1, (c + 1) & 1);
+                    else if (img + stride < n) issue(img + stride, 0, (c + 1) & 1);
+                }
+                mbar_wait(bar + (c & 1), (c >> 1) & 1);
+                const float *cellp = reinterpret_cast<const float *>(stage + static_cast<size_t>(c & 1) * cfg.stage_bytes) + lane * cfg.D;
+                if (valid[t]) decode_cell<0, 0>(cellp, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
+                ++c;
+            }
         }
         const int K = nms_warp<NS, false>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
                                           out_idx ? out_idx + img * cfg.M : nullptr);
@@ -629,7 +746,7 @@ static int fill_cfg(NmsCfg &cfg, int S, int B, int C, float iou_thr, float conf_
     cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
     cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
     cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr;
-    cfg.ws_bytes = 0; cfg.tbl_rows = C;
+    cfg.ws_bytes = 0; cfg.tbl_rows = C; cfg.stage_bytes = 0;
     return YH_OK;
 }
 
@@ -638,14 +755,29 @@ static int launch_direct(const float *pred, int64_t n, NmsCfg cfg, float *out_bo
                          cudaStream_t st)
 {
     cfg.ws_bytes = WarpWs<NS, false>::bytes(cfg.tbl_rows);
-    int wpb = 8;
-    while (wpb > 1 && static_cast<size_t>(wpb) * cfg.ws_bytes > 200 * 1024) wpb >>= 1;
-    const size_t smem = static_cast<size_t>(wpb) * cfg.ws_bytes;
-    if (smem > 227 * 1024) {
-        set_error("decode_nms: per-warp workspace %d B does not fit shared memory", cfg.ws_bytes);
+    const int64_t img_bytes = 4ll * cfg.M * cfg.D;
+    const int last_cells = cfg.M - 32 * ((cfg.M - 1) / 32);
+    // Measured on B200 (S=14, B=3, C=80, 131072 images): cells read straight from global/L1 with
+    // ~24 resident warps per SM 5.9 ms; per-slot LDG staging (10 warps/SM) 7.6 ms; per-warp
+    // cp.async.bulk double buffer (6 warps/SM) 8.0 ms - the per-image work is a serial chain per warp,
+    // so resident warps matter more than load efficiency.  Default = no staging; the other two stay
+    // selectable (YH_DIRECT_STAGE=1, YH_WARP_TMA=1) for experiments.
+    const bool bulk_ok = env_int("YH_WARP_TMA", 0) != 0 && reinterpret_cast<uintptr_t>(pred) % 16 == 0 &&
+                         img_bytes % 16 == 0 && (static_cast<int64_t>(last_cells) * cfg.D * 4) % 16 == 0 &&
+                         img_bytes > 12 * 1024;
+    const bool stage = bulk_ok || env_int("YH_DIRECT_STAGE", 0) != 0;
+    cfg.stage_bytes = stage ? ((32 * cfg.D * 4 + 15) & ~15) : 0;
+    const size_t per_warp = static_cast<size_t>(cfg.ws_bytes) + (bulk_ok ? 2 * cfg.stage_bytes + 16 : cfg.stage_bytes);
+    if (per_warp > 220 * 1024) {
+        set_error("decode_nms: per-warp workspace %zu B does not fit shared memory (C + 5B = %d too large)", per_warp, cfg.D);
         return YH_ERR_UNSUPPORTED;
     }
-    auto kern = decode_nms_direct_kernel<NS, CT, BT>;
+    // as many warps as fit one SM, in two blocks when there are enough of them
+    int warps_sm = static_cast<int>(std::min<size_t>(32, (224 * 1024) / per_warp));
+    int wpb = warps_sm >= 8 ? std::min(16, warps_sm / 2) : warps_sm;
+    if (wpb < 1) wpb = 1;
+    const size_t smem = static_cast<size_t>(wpb) * per_warp;
+    auto kern = bulk_ok ? decode_nms_warp_tma_kernel<NS, CT, BT> : decode_nms_direct_kernel<NS, CT, BT>;
     YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 1;
     YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
@@ -653,7 +785,7 @@ static int launch_direct(const float *pred, int64_t n, NmsCfg cfg, float *out_bo
     const int64_t want = (n + wpb - 1) / wpb;
     const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * per_sm));
     kern<<<grid, wpb * 32, smem, st>>>(pred, n, cfg, out_boxes, out_count, out_idx);
-    YH_LAUNCH_CHECK("decode_nms_direct_kernel");
+    YH_LAUNCH_CHECK(bulk_ok ? "decode_nms_warp_tma_kernel" : "decode_nms_direct_kernel");
     return YH_OK;
 }
 
@@ -780,7 +912,7 @@ extern "C" int yh_nms(const float *boxes, int64_t n, int M, float iou_thr, float
                "nms: boxes and out_boxes must be 8-byte aligned");
     NmsCfg cfg;
     cfg.S = 0; cfg.B = 0; cfg.C = 0; cfg.M = M; cfg.D = 6; cfg.inv_s = 0.f;
-    cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr; cfg.ws_bytes = 0; cfg.tbl_rows = 0;
+    cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.stage_bytes = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (pick_ns(M)) {
         case 1: return launch_nms_rows<1>(boxes, n, cfg, out_boxes, out_count, out_keep_idx, st);
@@ -798,7 +930,7 @@ extern "C" int yh_decode(const float *pred, int64_t n, int S, int B, int C, floa
     YH_REQUIRE(S >= 1 && B >= 1 && C >= 1 && n >= 0, "decode: bad sizes");
     cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
     cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
-    cfg.iou_thr = cfg.conf_thr = 0.f; cfg.ws_bytes = 0; cfg.tbl_rows = 0;
+    cfg.iou_thr = cfg.conf_thr = 0.f; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.stage_bytes = 0;
     if (n == 0) return YH_OK;
     YH_REQUIRE(pred && out_boxes, "decode: null pointer");
     YH_REQUIRE(reinterpret_cast<uintptr_t>(out_boxes) % 8 == 0, "decode: out_boxes must be 8-byte aligned");

@@ -107,6 +107,12 @@ def test_decode_nms_paths_agree(dev, monkeypatch):
     flat = _cuda(np.concatenate([np.zeros(2, F32), p.ravel()]), dev)[2:].reshape(p.shape)
     assert flat.data_ptr() % 16 == 8
     _check_nms(yu.decode_nms(flat, 20, 2, return_index=True), want, "8B-aligned")
+    for var in ("YH_DIRECT_STAGE", "YH_WARP_TMA"):           # the two staged variants of the direct kernel
+        monkeypatch.setenv("YH_TMA", "0"); monkeypatch.setenv(var, "1")
+        _check_nms(yu.decode_nms(_cuda(p, dev), 20, 2, return_index=True), want, var)
+        ps = F.synth_stress(8)
+        _check_nms(yu.decode_nms(_cuda(ps, dev), 80, 3, 0.5, 0.05, return_index=True), cport.decode_nms(ps, 80, 3, 0.5, 0.05), var + " stress")
+        monkeypatch.delenv("YH_TMA"); monkeypatch.delenv(var)
     for T, W, ST in ((4, 8, 2), (16, 16, 2), (8, 8, 5), (8, 16, 3), (4, 24, 5), (8, 24, 8), (2, 24, 8)):
         monkeypatch.setenv("YH_TMA_T", str(T)); monkeypatch.setenv("YH_TMA_W", str(W)); monkeypatch.setenv("YH_TMA_STAGES", str(ST))
         _check_nms(yu.decode_nms(_cuda(p, dev), 20, 2, return_index=True), want, f"tma T{T} W{W} ST{ST}")
