@@ -10,6 +10,7 @@
 // loss.py:189); TF sub-gradient conventions: clip passes on [0,1] inclusive, max/min send
 // ties to their first argument (the true box), sign(0) = 0.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "yh_common.cuh"
@@ -34,70 +35,158 @@ __device__ __forceinline__ double warp_sum(double v)
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
-// One tile = tile_cells consecutive cells; y_true / y_pred tiles are staged in shared memory with
-// coalesced 128-bit streaming loads.  Box part: one thread per cell (IoU, responsible box, the four
-// box/confidence terms and their gradients).  Class part: one warp per cell, lanes over classes
-// (conflict-free shared-memory rows).  The gradient goes back through the y_pred tile with 128-bit
-// stores.  Sums: per-thread float64 -> warp -> block partials; the last block to finish (ticket
-// counter) adds the partials of all blocks in index order and writes the six outputs, so there is a
-// single launch and the result does not depend on which block came last.
+// Persistent CTAs; each walks its tiles (tile_cells consecutive cells of y_true and y_pred) through a
+// kStages-deep shared-memory ring filled by cp.async.bulk (TMA, one elected thread, mbarrier
+// complete_tx), so the loads of tile i+1.. overlap the arithmetic of tile i; the gradient tile goes
+// back with a bulk shared->global store.  Tiles that are not 16-byte aligned/sized (tail, odd bases)
+// are moved with plain coalesced loads/stores by the whole CTA instead.
+//   pass A  thread per cell: cells without object and with an all-zero true box ("light", ~95 % of a
+//           VOC batch) only owe the no-object term on box 0 (every IoU is exactly +0 there, so the
+//           first-max responsible box is box 0, loss.py:136,197); the others are compacted (ballot)
+//   pass B  one thread per compacted "heavy" cell: IoUs, responsible box, the four box/confidence
+//           terms and their gradients
+//   pass C  class term and gradient, flat over (cell, class) so shared-memory rows are read
+//           conflict-free by consecutive lanes
+// Sums: per-thread float64 -> warp -> block partials; the last block to finish (ticket counter) adds
+// the partials of all blocks in index order and writes the six outputs: one launch, and the result
+// does not depend on which block came last.
+constexpr int kLossStages = 3;
+
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <bool kGrad>
 __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
                                                             LossCfg cfg, float *__restrict__ grad,
                                                             double *__restrict__ partials, unsigned *__restrict__ ticket,
                                                             float *__restrict__ out_terms)
 {
-    extern __shared__ float4 smem4[];
-    float *st = reinterpret_cast<float *>(smem4);
-    float *sp = st + static_cast<size_t>(cfg.tile_cells) * cfg.D;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int C = cfg.C, B = cfg.B, D = cfg.D;
+    const int tile_fl = cfg.tile_cells * D;
+    const uint32_t tile_bytes = static_cast<uint32_t>(tile_fl) * 4u;
+    float *ring = reinterpret_cast<float *>(smem);                     // [stage][0: y_true tile | 1: y_pred tile]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(kLossStages) * 2 * tile_bytes);
+    int *heavy = reinterpret_cast<int *>(full + kLossStages);           // [tile_cells] compacted heavy cells
     __shared__ double red[kLossThreads / 32][5];
     __shared__ double fin[5][26];
+    __shared__ int wcount[kLossThreads / 32];
     __shared__ bool is_last;
 
-    const int C = cfg.C, B = cfg.B, D = cfg.D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int64_t n_tiles = (cfg.n_cells + cfg.tile_cells - 1) / cfg.tile_cells;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(yt) | reinterpret_cast<uintptr_t>(yp) |
-                          (kGrad ? reinterpret_cast<uintptr_t>(grad) : 0)) % 16 == 0) &&
-                        ((static_cast<int64_t>(cfg.tile_cells) * D) % 4 == 0);
-    double sxy = 0, swh = 0, sob = 0, snb = 0, scl = 0;
+    const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool base_ok = ((reinterpret_cast<uintptr_t>(yt) | reinterpret_cast<uintptr_t>(yp) |
+                           (kGrad ? reinterpret_cast<uintptr_t>(grad) : 0)) % 16 == 0) && (tile_bytes % 16 == 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kLossStages; ++s) mbar_init(full + s, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t cell0 = tile * cfg.tile_cells;
-        const int cells = static_cast<int>(min(static_cast<int64_t>(cfg.tile_cells), cfg.n_cells - cell0));
+    // tile `it` of this CTA -> global tile index / cells; bulk path only for full, aligned tiles
+    auto tile_cells_of = [&](int64_t it) {
+        const int64_t cell0 = (blockIdx.x + it * gridDim.x) * cfg.tile_cells;
+        return static_cast<int>(min(static_cast<int64_t>(cfg.tile_cells), cfg.n_cells - cell0));
+    };
+    auto is_bulk = [&](int64_t it) { return base_ok && tile_cells_of(it) == cfg.tile_cells; };
+    auto issue = [&](int64_t it) {       // thread 0 only
+        const int s = static_cast<int>(it % kLossStages);
+        const int64_t off = (blockIdx.x + it * gridDim.x) * static_cast<int64_t>(tile_fl);
+        mbar_arrive_expect_tx(full + s, 2 * tile_bytes);
+        const uint64_t pol = l2_evict_first_policy();
+        bulk_g2s(ring + static_cast<size_t>(s) * 2 * tile_fl, yt + off, tile_bytes, full + s, pol);
+        bulk_g2s(ring + static_cast<size_t>(s) * 2 * tile_fl + tile_fl, yp + off, tile_bytes, full + s, pol);
+    };
+    if (threadIdx.x == 0)
+        for (int64_t it = 0; it < my_tiles && it < kLossStages - 1; ++it)
+            if (is_bulk(it)) issue(it);
+
+    double sxy = 0, swh = 0, sob = 0, snb = 0, scl = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int s = static_cast<int>(it % kLossStages);
+        const uint32_t ph = static_cast<uint32_t>((it / kLossStages) & 1);
+        const int64_t cell0 = (blockIdx.x + it * gridDim.x) * cfg.tile_cells;
+        const int cells = tile_cells_of(it);
         const int nfl = cells * D;
-        const float *gt = yt + cell0 * D;
-        const float *gp = yp + cell0 * D;
-        if (vec_ok) {
-            const int n4 = nfl >> 2;
-            const float4 *gt4 = reinterpret_cast<const float4 *>(gt);
-            const float4 *gp4 = reinterpret_cast<const float4 *>(gp);
-            float4 *st4 = reinterpret_cast<float4 *>(st);
-            float4 *sp4 = reinterpret_cast<float4 *>(sp);
-            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-                st4[i] = __ldcs(gt4 + i);
-                sp4[i] = __ldcs(gp4 + i);
+        float *st = ring + static_cast<size_t>(s) * 2 * tile_fl;
+        float *sp = st + tile_fl;
+        const bool bulk = is_bulk(it);
+        // refill the stage that tile it-1 used (its gradient store must have finished reading it)
+        if (threadIdx.x == 0) {
+            const int64_t nx = it + kLossStages - 1;
+            if (nx < my_tiles && is_bulk(nx)) {
+                bulk_store_wait_read_all();
+                issue(nx);
             }
-            for (int i = (n4 << 2) + threadIdx.x; i < nfl; i += blockDim.x) {
-                st[i] = gt[i];
-                sp[i] = gp[i];
-            }
+        }
+        if (bulk) {
+            mbar_wait(full + s, ph);
         } else {
+            if (threadIdx.x == 0) bulk_store_wait_read_all();
+            __syncthreads();
+            const float *gt = yt + cell0 * D, *gp = yp + cell0 * D;
             for (int i = threadIdx.x; i < nfl; i += blockDim.x) {
                 st[i] = gt[i];
                 sp[i] = gp[i];
             }
+            __syncthreads();
         }
-        __syncthreads();
 
-        // ---- box part: thread per cell; touches only channels >= C of the y_pred tile ----
-        for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
+        // ---- pass A: light cells + compaction of the heavy ones ----
+        int n_heavy = 0;
+        for (int c0 = 0; c0 < cells; c0 += blockDim.x) {
+            const int cell = c0 + threadIdx.x;
+            bool hv = false;
+            if (cell < cells) {
+                const float *t = st + cell * D;
+                float *p = sp + cell * D;
+                const float obj = t[C];
+                hv = (obj != 0.0f) || (t[C + 1] != 0.0f) || (t[C + 2] != 0.0f) || (t[C + 3] != 0.0f) || (t[C + 4] != 0.0f);
+                if (!hv) {
+                    const float c = p[C];                                     // responsible = box 0
+                    const float noobj = __fsub_rn(1.0f, obj);                 // loss.py:163
+                    const float z = __fsub_rn(0.0f, c);
+                    snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));   // loss.py:197
+                    if (kGrad) {
+                        for (int j = C + 1; j < D; ++j) p[j] = 0.f;
+                        p[C] = cfg.ln * 2.0f * noobj * c;
+                    }
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hv);
+            if (lane == 0) wcount[warp] = __popc(bal);
+            __syncthreads();
+            int base = n_heavy;
+            for (int w = 0; w < warp; ++w) base += wcount[w];
+            if (hv) heavy[base + __popc(bal & ((1u << lane) - 1u))] = cell;
+            for (int w = 0; w < nwarp; ++w) n_heavy += wcount[w];
+            __syncthreads();
+        }
+
+        // ---- pass B: heavy cells, one thread each; cell h goes to warp h % nwarp so that the few
+        //      heavy cells of a tile (long dependent chains: divisions, square roots) run in parallel
+        //      on different warps instead of side by side in one ----
+        for (int h = lane * nwarp + warp; h < n_heavy; h += 32 * nwarp) {
+            const int cell = heavy[h];
             const float *t = st + cell * D;
             float *p = sp + cell * D;
             const float obj = t[C];                                           // loss.py:162
             const float tx = t[C + 1], ty = t[C + 2], tw = t[C + 3], th = t[C + 4];
-            // responsible box: first max of IoU(true, pred_b)               // loss.py:126-137
-            int k = 0;
+            int k = 0;                                                        // loss.py:126-137
             float u = iou_ref(tx, ty, tw, th, p[C + 1], p[C + 2], p[C + 3], p[C + 4]);
             for (int b = 1; b < B; ++b) {
                 const float *q = p + C + 5 * b;
@@ -105,31 +194,30 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
                 if (v > u) { u = v; k = b; }
             }
             float *q = p + C + 5 * k;
-            const float c = q[0], px = q[1], py = q[2], pw = q[3], ph = q[4];
-            const float noobj = __fsub_rn(1.0f, obj);                         // loss.py:163
+            const float c = q[0], px = q[1], py = q[2], pw = q[3], ph_ = q[4];
+            const float noobj = __fsub_rn(1.0f, obj);
             const float z = __fsub_rn(0.0f, c);
-            snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));    // loss.py:197
-            float g_c = cfg.ln * 2.0f * noobj * c;
-            float g_x = 0.f, g_y = 0.f, g_w = 0.f, g_h = 0.f;
-            if (obj != 0.0f) {
-                // forward terms (float32 element-wise, as the reference)
-                const float dx = __fsub_rn(tx, px), dy = __fsub_rn(ty, py);
-                sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dx, dx)));    // loss.py:171
-                sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dy, dy)));
-                const float sw = sgn(pw), sh = sgn(ph);
-                const float rw = __fsqrt_rn(__fadd_rn(fabsf(pw), 1e-6f)), rh = __fsqrt_rn(__fadd_rn(fabsf(ph), 1e-6f));
-                const float dw = __fsub_rn(__fsqrt_rn(tw), __fmul_rn(sw, rw));    // loss.py:176-178
-                const float dh = __fsub_rn(__fsqrt_rn(th), __fmul_rn(sh, rh));
-                swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dw, dw)));
-                swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dh, dh)));
-                const float e = __fsub_rn(u, c);
-                sob += static_cast<double>(__fmul_rn(obj, __fmul_rn(e, e)));      // loss.py:189
-                if (kGrad) {
+            snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));
+            const float dx = __fsub_rn(tx, px), dy = __fsub_rn(ty, py);
+            sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dx, dx)));    // loss.py:171
+            sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dy, dy)));
+            const float sw = sgn(pw), sh = sgn(ph_);
+            const float rw = __fsqrt_rn(__fadd_rn(fabsf(pw), 1e-6f)), rh = __fsqrt_rn(__fadd_rn(fabsf(ph_), 1e-6f));
+            const float dw = __fsub_rn(__fsqrt_rn(tw), __fmul_rn(sw, rw));    // loss.py:176-178
+            const float dh = __fsub_rn(__fsqrt_rn(th), __fmul_rn(sh, rh));
+            swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dw, dw)));
+            swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dh, dh)));
+            const float e = __fsub_rn(u, c);
+            sob += static_cast<double>(__fmul_rn(obj, __fmul_rn(e, e)));      // loss.py:189
+            if (kGrad) {
+                float g_c = cfg.ln * 2.0f * noobj * c;
+                float g_x = 0.f, g_y = 0.f, g_w = 0.f, g_h = 0.f;
+                if (obj != 0.0f) {
                     // IoU pieces again, with their partial derivatives
                     const float x1n = (tx - tw) * 0.5f, x1x = (tx + tw) * 0.5f;
                     const float y1n = (ty - th) * 0.5f, y1x = (ty + th) * 0.5f;
                     const float x2n = (px - pw) * 0.5f, x2x = (px + pw) * 0.5f;
-                    const float y2n = (py - ph) * 0.5f, y2x = (py + ph) * 0.5f;
+                    const float y2n = (py - ph_) * 0.5f, y2x = (py + ph_) * 0.5f;
                     const float ddx = fminf(x1x, x2x) - fmaxf(x1n, x2n);
                     const float ddy = fminf(y1x, y2x) - fmaxf(y1n, y2n);
                     const float cw = clip01(ddx), ch = clip01(ddy);
@@ -157,38 +245,43 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
                     g_w = -2.0f * cfg.lc * obj * dw * (sw * sw) / (2.0f * rw) + e2 * du_dpw;
                     g_h = -2.0f * cfg.lc * obj * dh * (sh * sh) / (2.0f * rh) + e2 * du_dph;
                 }
-            }
-            if (kGrad) {
                 for (int j = C; j < D; ++j) p[j] = 0.f;
                 q[0] = g_c; q[1] = g_x; q[2] = g_y; q[3] = g_w; q[4] = g_h;
             }
         }
-        // ---- class part: warp per cell, lanes over classes; touches only channels < C ----
-        for (int cell = warp; cell < cells; cell += nwarp) {
-            const float *t = st + cell * D;
-            float *p = sp + cell * D;
-            const float obj = t[C];
-            for (int j = lane; j < C; j += 32) {                              // loss.py:206
-                const float d = __fsub_rn(t[j], p[j]);
-                if (obj != 0.0f) scl += static_cast<double>(__fmul_rn(obj, __fmul_rn(d, d)));
-                if (kGrad) p[j] = (obj != 0.0f) ? -2.0f * obj * d : 0.0f;
+
+        // ---- pass C: class term, flat over (cell, class); touches only channels < C ----
+        {
+            const int total = cells * C;
+            int cell = threadIdx.x / C, j = threadIdx.x % C;
+            const int dc = blockDim.x / C, dj = blockDim.x % C;
+            for (int e_ = threadIdx.x; e_ < total; e_ += blockDim.x) {
+                const float obj = st[cell * D + C];
+                float *pp = sp + cell * D + j;
+                if (obj != 0.0f) {                                            // loss.py:206
+                    const float d = __fsub_rn(st[cell * D + j], *pp);
+                    scl += static_cast<double>(__fmul_rn(obj, __fmul_rn(d, d)));
+                    if (kGrad) *pp = -2.0f * obj * d;
+                } else if (kGrad) {
+                    *pp = 0.0f;
+                }
+                cell += dc; j += dj;
+                if (j >= C) { j -= C; ++cell; }
             }
         }
+        if (kGrad && bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my tile writes -> async proxy
         __syncthreads();
         if (kGrad) {
             float *gg = grad + cell0 * D;
-            if (vec_ok) {
-                const int n4 = nfl >> 2;
-                float4 *gg4 = reinterpret_cast<float4 *>(gg);
-                const float4 *sp4 = reinterpret_cast<const float4 *>(sp);
-                for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcs(gg4 + i, sp4[i]);
-                for (int i = (n4 << 2) + threadIdx.x; i < nfl; i += blockDim.x) gg[i] = sp[i];
+            if (bulk) {
+                if (threadIdx.x == 0) bulk_s2g(gg, sp, tile_bytes);
             } else {
                 for (int i = threadIdx.x; i < nfl; i += blockDim.x) gg[i] = sp[i];
+                __syncthreads();
             }
         }
-        __syncthreads();
     }
+    if (threadIdx.x == 0) bulk_store_wait_all();
 
     // stage 1 of the deterministic reduction: lanes -> warp -> block, fixed order
     sxy = warp_sum(sxy); swh = warp_sum(swh); sob = warp_sum(sob); snb = warp_sum(snb); scl = warp_sum(scl);
@@ -264,9 +357,11 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LossCfg cfg;
     cfg.B = B; cfg.C = C; cfg.D = C + 5 * B; cfg.lc = lambda_coord; cfg.ln = lambda_noobj; cfg.n_cells = n_cells;
-    int tile = 128;
-    while (tile > 32 && static_cast<size_t>(tile) * cfg.D * 8 > 100 * 1024) tile >>= 1;
-    const size_t smem = static_cast<size_t>(tile) * cfg.D * 8;
+    int tile = 128;                      // cells per tile; ring = kLossStages x (y_true + y_pred tile)
+    auto smem_of = [&](int tl) { return static_cast<size_t>(kLossStages) * 2 * tl * cfg.D * 4 + kLossStages * 8 + static_cast<size_t>(tl) * 4 + 64; };
+    static const int smem_cap_kb = [] { const char *v = getenv("YH_LOSS_SMEM_KB"); return (v && *v) ? atoi(v) : 72; }();
+    while (tile > 16 && smem_of(tile) > static_cast<size_t>(smem_cap_kb) * 1024) tile >>= 1;
+    const size_t smem = smem_of(tile);
     if (smem > 227 * 1024) {
         set_error("loss: C + 5B = %d too large for the shared-memory tile", cfg.D);
         return YH_ERR_UNSUPPORTED;
