@@ -5,14 +5,16 @@ import this module; only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do, and only as the
 checker or the timed CPU baseline - never as the product path.
 
-PARITY UNPINNED: the reference (myungsanglee/Keras-Object-Detection) holds no
-tests, no golden outputs and cannot be imported here (TensorFlow is absent from
-this image and from the wheelhouse; even its ``*_numpy`` twins call TF and use the
-removed ``np.int``).  This file therefore RESTATES the reference algorithm in
-float32 NumPy, loop for loop, each function citing the ``yolo_v1/*.py`` lines it
-follows (paths relative to /root/reference).  The only fixtures the reference
-holds are the inputs of its ``__main__`` smoke blocks; ``tests/golden`` pins this
-oracle's outputs on them (hand-derivable values).
+PINNING: the reference (myungsanglee/Keras-Object-Detection) holds no tests and no
+golden outputs, and TensorFlow is absent from this image and its wheelhouse (even the
+``*_numpy`` twins call TF and use the removed ``np.int``).  This file RESTATES the
+reference algorithm in float32 NumPy, loop for loop, each function citing the
+``yolo_v1/*.py`` lines it follows (paths relative to /root/reference).  It is pinned
+against ``tests/golden/ref_golden.npz`` = outputs of the reference's OWN utils.py /
+loss.py, executed unmodified in the build container on a NumPy stand-in for the TF
+primitives (tests/golden/make_ref_golden.py, tests/golden/tfshim); see
+tests/test_ref_golden.py.  Still unpinned: that real TensorFlow kernels agree with
+the library semantics below, and the stale metric.py/tmp.py variants (restated only).
 
 Third-party semantics relied on (tensorflow, unpinned; ~2.4-2.6 by API use):
   * ``tf.argsort(direction='DESCENDING')`` is stable (lower index first on ties)

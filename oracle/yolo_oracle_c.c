@@ -3,11 +3,14 @@
  * TEST INFRASTRUCTURE ONLY - the checker and the timed CPU baseline.  Nothing in
  * the product (keras-object-detection_b200/) links, loads or calls this file.
  *
- * PARITY UNPINNED: the reference (myungsanglee/Keras-Object-Detection) is pure
- * Python on TensorFlow, which is absent from this image, and it holds no tests or
- * golden outputs.  This file restates the reference loops in float32 C (compile
- * with -ffp-contract=off, never -ffast-math) and is cross-checked against the
- * NumPy restatement oracle/yolo_oracle.py in tests/test_oracle.py.
+ * PINNING: the reference (myungsanglee/Keras-Object-Detection) is pure Python on
+ * TensorFlow, which is absent from this image, and it holds no tests or golden
+ * outputs.  This file restates the reference loops in float32 C (compile with
+ * -ffp-contract=off, never -ffast-math).  It is checked against the NumPy
+ * restatement oracle/yolo_oracle.py (tests/test_oracle.py) and against
+ * tests/golden/ref_golden.npz = outputs of the reference's own utils.py/loss.py run
+ * on a NumPy stand-in for TF (tests/test_ref_golden.py).  Real TensorFlow kernels
+ * remain unpinned.
  * Citations are relative to /root/reference/yolo_v1/.
  */
 #include <math.h>

@@ -1,0 +1,145 @@
+"""Regenerates tests/golden/ref_golden.npz: what the REFERENCE'S OWN SOURCE returns.
+
+Runs only in the build container (it reads /root/reference, which the GPU box does not have).
+`yolo_v1/utils.py` and `yolo_v1/loss.py` are imported unmodified from /root/reference with
+`tests/golden/tfshim` first on sys.path, i.e. every line of the reference executes, on top of a
+NumPy stand-in for the TensorFlow primitives it calls (TensorFlow itself is absent from this image
+and its wheelhouse; see the stand-in's docstring for the exact semantics restated and
+DESIGN.md section 5 for what that does and does not pin).  Inputs are stored next to the outputs so
+the tests do not depend on NumPy's generator streams.
+
+    python tests/golden/make_ref_golden.py
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("YH_REFERENCE", "/root/reference/yolo_v1")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(HERE, "tfshim"))
+warnings.simplefilter("ignore")          # np.trapz deprecation (utils.py:444)
+
+import tensorflow as tf  # noqa: E402  (the stand-in)
+import torch  # noqa: E402
+
+assert "numpy-standin" in tf.__version__
+import loss as RL  # noqa: E402   /root/reference/yolo_v1/loss.py
+import utils as RU  # noqa: E402  /root/reference/yolo_v1/utils.py
+
+from tests import fixtures as F  # noqa: E402
+
+assert os.path.realpath(RU.__file__).startswith(os.path.realpath(REF)), RU.__file__
+F32 = np.float32
+
+
+def T(a):
+    return tf.cast(np.asarray(a), tf.float32)
+
+
+def nms_batch(decoded, iou_thr=0.5, conf_thr=0.4):
+    """Reference per-image loop (utils.py:474-480) -> padded rows + counts."""
+    n, m = decoded.shape[0], decoded.shape[1]
+    rows = np.zeros((n, m, 6), F32)
+    cnt = np.zeros((n,), np.int32)
+    for i in range(n):
+        k = np.asarray(RU.non_max_suppression(decoded[i], iou_threshold=iou_thr, conf_threshold=conf_thr))
+        k = k.reshape(-1, 6)
+        rows[i, :len(k)] = k
+        cnt[i] = len(k)
+    return rows, cnt
+
+
+def evaluator(batches, C, B):
+    ev = RU.MeanAveragePrecision(C, B)
+    for yt, yp in batches:
+        ev.update_state(T(yt), T(yp))
+    m = np.float32(np.asarray(ev.result()))
+    return m, np.asarray(ev.all_true_boxes_variable), np.asarray(ev.all_pred_boxes_variable)
+
+
+def main():
+    g = {}
+    # ---- the reference's own fixtures ------------------------------------------------------
+    yt, yp = F.utils_demo()                                            # utils.py:717-769
+    g["demo_yt"], g["demo_yp"] = yt, yp
+    dec = RU.decode_predictions(T(yp), 3, 2)
+    g["demo_decode_pred"] = np.asarray(dec)
+    g["demo_nms_pred"] = np.asarray(RU.non_max_suppression(dec[0]))
+    g["demo_nms_true"] = np.asarray(RU.non_max_suppression(RU.decode_predictions(T(yt), 3, 2)[0]))
+    g["demo_map"], g["demo_true_rows"], g["demo_pred_rows"] = evaluator([(yt, yp)], 3, 2)
+    lt, lp = F.loss_demo()                                             # loss.py:219-237
+    g["loss_demo_yt"], g["loss_demo_yp"] = lt, lp
+    g["loss_demo_total"] = np.float32(np.asarray(RL.YoloV1Loss(num_classes=3, num_boxes=2)(T(lt), T(lp))))
+
+    # ---- IoU: random pairs, degenerate and negative extents --------------------------------
+    rng = np.random.Generator(np.random.PCG64(42))
+    a = rng.random((4096, 4), dtype=F32)
+    b = rng.random((4096, 4), dtype=F32)
+    a[:64, 2:] *= F32(-1)                      # negative w,h: |area| path (utils.py:40-41)
+    b[64:128] = a[64:128]                      # identical boxes
+    a[128:192, 2:] = 0                         # zero area
+    b[192:256, :2] += F32(3)                   # extents that clip at 1 / disjoint boxes
+    g["iou_a"], g["iou_b"] = a, b
+    g["iou_out"] = np.asarray(RU.intersection_over_union(T(a), T(b)))
+
+    # ---- decode + NMS (S=7: the reference hard-codes 7, utils.py:184,200-216) --------------
+    for name, p, thr in (("dense", F.synth_dense(12, seed=1234), (0.5, 0.4)),
+                         ("sparse", F.synth_sparse(48, seed=2025), (0.5, 0.4)),
+                         ("quant", F.synth_quantised(12, 7, 2, 20, seed=5), (0.5, 0.4)),
+                         ("quant_lo", F.synth_quantised(6, 7, 2, 20, seed=6), (0.25, 0.05)),
+                         ("b3c5", F.synth_dense(6, 7, 3, 5, seed=77), (0.3, 0.2))):
+        B = 3 if name == "b3c5" else 2
+        C = 5 if name == "b3c5" else 20
+        if name == "sparse":
+            p[5] = 0                            # an image with no candidate at all
+            p[6, ..., C] = F32(0.4)             # conf == threshold exactly: strict > (utils.py:95)
+            p[6, ..., C + 5] = F32(0.1)
+        dec = np.asarray(RU.decode_predictions(T(p), C, B))
+        rows, cnt = nms_batch(tf.cast(dec, tf.float32), *thr)
+        g[f"{name}_in"], g[f"{name}_decode"], g[f"{name}_rows"], g[f"{name}_count"] = p, dec, rows, cnt
+        g[f"{name}_thr"] = np.array(thr, F32)
+
+    # ---- loss (+ gradient of the same source under torch autograd, off ties) ---------------
+    yt = F.synth_labels(16, seed=7)
+    yp = F.synth_loss_pred(yt.shape, seed=7)
+    g["loss16_yt"], g["loss16_yp"] = yt, yp
+    g["loss16_total"] = np.float32(np.asarray(RL.YoloV1Loss(20, 2)(T(yt), T(yp))))
+    tp = torch.from_numpy(yp.copy()).requires_grad_(True)
+    tot = RL.YoloV1Loss(20, 2)(torch.from_numpy(yt), tp)
+    tot.backward()
+    g["loss16_total_torch"] = np.float32(tot.item())
+    g["loss16_grad_torch"] = tp.grad.numpy().astype(F32)
+    yt = F.synth_labels(4, 7, 3, 5, seed=3)
+    yp = F.synth_loss_pred(yt.shape, seed=3)
+    g["loss_b3_yt"], g["loss_b3_yp"] = yt, yp
+    g["loss_b3_total"] = np.float32(np.asarray(RL.YoloV1Loss(5, 3)(T(yt), T(yp))))
+
+    # ---- evaluator + mAP -------------------------------------------------------------------
+    yt = F.synth_labels(40, seed=11)
+    yp = F.synth_map_pred(yt)
+    g["map40_yt"], g["map40_yp"] = yt, yp
+    g["map40_map"], g["map40_true_rows"], g["map40_pred_rows"] = evaluator([(yt[:25], yp[:25]), (yt[25:], yp[25:])], 20, 2)
+    # direct call on hand-made rows: class without GT, class without detections, two detections
+    # fighting for one GT, equal confidences (stable order), detection in an image without GT
+    true_rows = np.array([[0, 0, 1, .5, .5, .2, .2], [0, 0, 1, .2, .2, .1, .1], [1, 0, 1, .5, .5, .2, .2],
+                          [1, 2, 1, .3, .3, .2, .2], [2, 2, 1, .6, .6, .3, .3]], F32)
+    pred_rows = np.array([[0, 0, .9, .5, .5, .2, .2], [0, 0, .9, .51, .5, .2, .2], [0, 0, .8, .2, .2, .1, .1],
+                          [1, 0, .7, .9, .9, .1, .1], [3, 0, .95, .5, .5, .2, .2], [1, 2, .6, .3, .3, .2, .2],
+                          [2, 2, .6, .6, .6, .3, .3], [2, 2, .6, .6, .61, .3, .3], [0, 1, .99, .5, .5, .2, .2]], F32)
+    g["rows_true"], g["rows_pred"] = true_rows, pred_rows
+    g["rows_map"] = np.float32(np.asarray(RU.mean_average_precision(T(true_rows), T(pred_rows), 4)))
+    g["rows_map_thr03"] = np.float32(np.asarray(RU.mean_average_precision(T(true_rows), T(pred_rows), 4, iou_threshold=0.3)))
+
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "ref_golden.npz")
+    np.savez_compressed(out, **g)
+    for k, v in g.items():
+        print(f"{k:22s} {str(np.asarray(v).shape):18s} {np.asarray(v).dtype}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+"""Pins against tests/golden/ref_golden.npz = outputs of the reference's OWN source files
+(yolo_v1/utils.py, yolo_v1/loss.py) executed in the build container on a NumPy stand-in for
+TensorFlow (tests/golden/make_ref_golden.py, tests/golden/tfshim).
+
+CPU part: the oracle (NumPy restatement and its C port) must reproduce those outputs.
+GPU part (-m gpu): the CUDA path, through the reference's call surface, must reproduce them.
+Bars (BASELINE.json north_star): IoU / decoded rows / kept rows / counts bit-exact; loss within
+1e-5 relative; gradient within 1e-4 (float32 autograd vs closed form); mAP within 1e-6."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport
+from oracle import yolo_oracle as O
+
+R = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden.npz"))
+F32 = np.float32
+NMS_CASES = [("dense", 20, 2), ("sparse", 20, 2), ("quant", 20, 2), ("quant_lo", 20, 2), ("b3c5", 5, 3)]
+
+
+def _kept(rows, cnt):
+    m = np.arange(rows.shape[1])[None, :] < np.asarray(cnt)[:, None]
+    return rows[m]
+
+
+# ------------------------------------------------------------------ CPU: oracle vs reference
+def test_oracle_iou_matches_reference_source():
+    assert np.array_equal(O.intersection_over_union(R["iou_a"], R["iou_b"]), R["iou_out"])
+    assert np.array_equal(cport.iou(R["iou_a"], R["iou_b"]).reshape(-1, 1), R["iou_out"])
+
+
+@pytest.mark.parametrize("name,C,B", NMS_CASES, ids=[c[0] for c in NMS_CASES])
+def test_oracle_decode_nms_matches_reference_source(name, C, B):
+    p, it, ct = R[f"{name}_in"], float(R[f"{name}_thr"][0]), float(R[f"{name}_thr"][1])
+    assert np.array_equal(O.decode_predictions(p, C, B), R[f"{name}_decode"])
+    assert np.array_equal(cport.decode(p, C, B), R[f"{name}_decode"])
+    for fn in (O.decode_nms, cport.decode_nms):
+        rows, cnt, _ = fn(p, C, B, it, ct)
+        assert np.array_equal(cnt, R[f"{name}_count"]), name
+        assert np.array_equal(_kept(rows, cnt), _kept(R[f"{name}_rows"], R[f"{name}_count"])), name
+    if name == "sparse":
+        assert R["sparse_count"][5] == 0 and R["sparse_count"][6] == 0      # empty image; conf == thr is dropped
+
+
+def test_oracle_reference_fixtures():
+    yp, yt = R["demo_yp"], R["demo_yt"]
+    assert np.array_equal(O.decode_predictions(yp, 3, 2), R["demo_decode_pred"])
+    assert np.array_equal(O.non_max_suppression(O.decode_predictions(yp, 3, 2)[0]), R["demo_nms_pred"])
+    assert np.array_equal(O.non_max_suppression(O.decode_predictions(yt, 3, 2)[0]), R["demo_nms_true"])
+    ev = O.MeanAveragePrecision(3, 2)
+    ev.update_state(yt, yp)
+    assert np.array_equal(ev.all_true_boxes_variable, R["demo_true_rows"])
+    assert np.array_equal(ev.all_pred_boxes_variable, R["demo_pred_rows"])
+    assert abs(float(ev.result()) - float(R["demo_map"])) <= 1e-6
+    L = O.yolo_v1_loss(R["loss_demo_yt"], R["loss_demo_yp"], 3, 2)
+    assert abs(L["total_f64"] - float(R["loss_demo_total"])) <= 1e-5 * float(R["loss_demo_total"])
+
+
+def test_oracle_loss_and_gradient_match_reference_source():
+    for key, C, B in (("loss16", 20, 2), ("loss_b3", 5, 3)):
+        L = O.yolo_v1_loss(R[f"{key}_yt"], R[f"{key}_yp"], C, B)
+        want = float(R[f"{key}_total"])
+        assert abs(L["total_f64"] - want) <= 1e-5 * abs(want), key
+        assert abs(float(cport.loss(R[f"{key}_yt"], R[f"{key}_yp"], C, B)[5]) - want) <= 1e-5 * abs(want), key
+    g = O.yolo_v1_loss_grad(R["loss16_yt"], R["loss16_yp"])
+    np.testing.assert_allclose(g, R["loss16_grad_torch"], rtol=1e-4, atol=1e-4)
+
+
+def test_oracle_map_matches_reference_source():
+    ev = O.MeanAveragePrecision(20, 2)
+    ev.update_state(R["map40_yt"][:25], R["map40_yp"][:25])
+    ev.update_state(R["map40_yt"][25:], R["map40_yp"][25:])
+    assert np.array_equal(ev.all_true_boxes_variable, R["map40_true_rows"])
+    assert np.array_equal(ev.all_pred_boxes_variable, R["map40_pred_rows"])
+    assert abs(float(ev.result()) - float(R["map40_map"])) <= 1e-6
+    assert abs(float(cport.mean_average_precision(R["map40_true_rows"], R["map40_pred_rows"], 20)[0]) - float(R["map40_map"])) <= 1e-6
+    for key, thr in (("rows_map", 0.5), ("rows_map_thr03", 0.3)):
+        got = O.mean_average_precision(R["rows_true"], R["rows_pred"], 4, thr)
+        assert abs(float(got) - float(R[key])) <= 1e-6, (key, got, R[key])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/yolo_v1"), reason="reference sources only exist in the build container")
+def test_committed_golden_is_what_the_reference_source_returns(tmp_path):
+    """Re-executes the reference's files (make_ref_golden.py) and compares with the committed file."""
+    import subprocess
+    import sys
+    out = str(tmp_path / "regen.npz")
+    script = os.path.join(os.path.dirname(__file__), "golden", "make_ref_golden.py")
+    subprocess.check_call([sys.executable, script, out], stdout=subprocess.DEVNULL)
+    new = np.load(out)
+    assert sorted(new.files) == sorted(R.files)
+    for k in R.files:
+        assert np.array_equal(new[k], R[k]), k
+
+
+# ------------------------------------------------------------------ GPU: CUDA path vs reference
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _cuda(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.gpu
+def test_cuda_iou_matches_reference_source(dev):
+    from yolohot import utils as yu
+    out = yu.intersection_over_union(_cuda(R["iou_a"], dev), _cuda(R["iou_b"], dev)).cpu().numpy()
+    assert out.shape == R["iou_out"].shape and np.array_equal(out, R["iou_out"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,C,B", NMS_CASES, ids=[c[0] for c in NMS_CASES])
+def test_cuda_decode_nms_matches_reference_source(dev, name, C, B):
+    from yolohot import utils as yu
+    p, it, ct = R[f"{name}_in"], float(R[f"{name}_thr"][0]), float(R[f"{name}_thr"][1])
+    dec = yu.decode_predictions(_cuda(p, dev), C, B)
+    assert np.array_equal(dec.cpu().numpy(), R[f"{name}_decode"])
+    rows, cnt = yu.decode_nms(_cuda(p, dev), C, B, it, ct)[:2]
+    rows, cnt = rows.cpu().numpy(), cnt.cpu().numpy()
+    assert np.array_equal(cnt, R[f"{name}_count"])
+    assert np.array_equal(_kept(rows, cnt), _kept(R[f"{name}_rows"], R[f"{name}_count"]))
+    # the reference's own per-image call (utils.py:475): decoded rows of one image -> kept rows
+    for i in range(min(4, p.shape[0])):
+        k = yu.non_max_suppression(dec[i], it, ct).cpu().numpy()
+        assert np.array_equal(k, R[f"{name}_rows"][i, :R[f"{name}_count"][i]])
+
+
+@pytest.mark.gpu
+def test_cuda_reference_fixtures(dev):
+    from yolohot import loss as yloss, utils as yu
+    yp, yt = _cuda(R["demo_yp"], dev), _cuda(R["demo_yt"], dev)
+    assert np.array_equal(yu.non_max_suppression(yu.decode_predictions(yp, 3, 2)[0]).cpu().numpy(), R["demo_nms_pred"])
+    assert np.array_equal(yu.non_max_suppression(yu.decode_predictions(yt, 3, 2)[0]).cpu().numpy(), R["demo_nms_true"])
+    ev = yu.MeanAveragePrecision(3, 2)
+    ev.update_state(yt, yp)
+    assert np.array_equal(ev.all_true_boxes_variable.cpu().numpy(), R["demo_true_rows"])
+    assert np.array_equal(ev.all_pred_boxes_variable.cpu().numpy(), R["demo_pred_rows"])
+    assert abs(float(ev.result()) - float(R["demo_map"])) <= 1e-6
+    tot = float(yloss.YoloV1Loss(3, 2)(_cuda(R["loss_demo_yt"], dev), _cuda(R["loss_demo_yp"], dev)))
+    assert abs(tot - float(R["loss_demo_total"])) <= 1e-5 * float(R["loss_demo_total"])
+
+
+@pytest.mark.gpu
+def test_cuda_loss_and_gradient_match_reference_source(dev):
+    from yolohot import loss as yloss
+    for key, C, B in (("loss16", 20, 2), ("loss_b3", 5, 3)):
+        yp = _cuda(R[f"{key}_yp"], dev).requires_grad_(True)
+        tot = yloss.YoloV1Loss(C, B)(_cuda(R[f"{key}_yt"], dev), yp)
+        want = float(R[f"{key}_total"])
+        assert abs(float(tot.detach()) - want) <= 1e-5 * abs(want), key
+        if key == "loss16":
+            tot.backward()
+            np.testing.assert_allclose(yp.grad.cpu().numpy(), R["loss16_grad_torch"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_cuda_map_matches_reference_source(dev):
+    from yolohot import utils as yu
+    ev = yu.MeanAveragePrecision(20, 2)
+    ev.update_state(_cuda(R["map40_yt"][:25], dev), _cuda(R["map40_yp"][:25], dev))
+    ev.update_state(_cuda(R["map40_yt"][25:], dev), _cuda(R["map40_yp"][25:], dev))
+    assert np.array_equal(ev.all_true_boxes_variable.cpu().numpy(), R["map40_true_rows"])
+    assert np.array_equal(ev.all_pred_boxes_variable.cpu().numpy(), R["map40_pred_rows"])
+    assert abs(float(ev.result()) - float(R["map40_map"])) <= 1e-6
+    for key, thr in (("rows_map", 0.5), ("rows_map_thr03", 0.3)):
+        got = yu.mean_average_precision(_cuda(R["rows_true"], dev), _cuda(R["rows_pred"], dev), 4, thr)
+        assert abs(float(got) - float(R[key])) <= 1e-6, (key, float(got), R[key])
