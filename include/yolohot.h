@@ -122,6 +122,32 @@ YH_API int yh_map_match(const float *true_rows, int64_t nt, const float *pred_ro
 YH_API int yh_map_reduce(const uint64_t *keys, const uint8_t *tp, int64_t nrec,
                   const int32_t *gt_per_class, int C, float *out_ap, float *out_map, void *stream);
 
+/* ---- callers either side of the path ------------------------ */
+
+/* N2 - dataset.py:88-112 YoloV1Generator._get_labels, batched.  boxes (total, 5) FLOAT64 rows
+ * [cx, cy, w, h, class] (what dataset.py:114-123 _get_boxes / albumentations hand over);
+ * offsets (n+1) int64, image i owns rows [offsets[i], offsets[i+1]).  out (n,S,S,C+5B) float32
+ * is written completely (zeros + labels): first box wins a cell (:107), x from the column, y from
+ * the row (:101-105), float64 arithmetic then the float32 cast of :85.  Python index rules are
+ * kept (cell/class indices wrap once when negative); a box whose indices would raise IndexError
+ * in the reference is skipped and counted in *out_bad (device int32, nullable). */
+YH_API int yh_encode_labels(const double *boxes, const int64_t *offsets, int64_t n, int S, int B, int C,
+                     float *out, int32_t *out_bad, void *stream);
+
+/* N3 - head adapter (train.py:208, model.py:107).  A flat (N, S*S*(C+5B)) head output IS the
+ * (N,S,S,C+5B) tensor - pass the same pointer to the entry points above.  A half-precision head
+ * is widened exactly to float32 first: src_dtype YH_DTYPE_F16 / YH_DTYPE_BF16, n elements. */
+#define YH_DTYPE_F16 1
+#define YH_DTYPE_BF16 2
+YH_API int yh_head_to_f32(const void *src, int src_dtype, int64_t n, float *dst, void *stream);
+
+/* N4 - utils.py:652-655 (get_tagged_img / get_grid_tagged_img): pixel corners of kept rows,
+ * xmin = int((cx - w/2) * width), ... in float32, int() truncating toward zero.
+ * rows (n, M, 6) as written by yh_nms / yh_decode_nms, count (n) nullable; out (n, M, 4) int32
+ * [xmin, ymin, xmax, ymax], rows at or beyond count[i] are set to -1. */
+YH_API int yh_pixel_boxes(const float *rows, const int32_t *count, int64_t n, int M, int width, int height,
+                   int32_t *out, void *stream);
+
 /* ---- DLPack front ends ----------------------------------------------------------------
  * Same operations taking DLManagedTensor* (what `tensor.__dlpack__()` capsules hold, so
  * torch / TF-Keras / CuPy tensors pass zero-copy).  They validate device (kDLCUDA, the

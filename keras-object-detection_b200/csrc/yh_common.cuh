@@ -141,6 +141,29 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// shared -> global bulk copy (TMA store, bulk async-group completion).  src/dst 16-byte aligned,
+// bytes a multiple of 16.  Generic-proxy writes to the source must be made visible to the async
+// proxy first (fence.proxy.async.shared::cta by the writers, then a barrier).
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 #endif  // __CUDACC__
 
 }  // namespace yh

@@ -52,22 +52,6 @@ __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0
 // does not depend on which block came last.
 constexpr int kLossStages = 3;
 
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
-                 "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read_all()
-{
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_all()
-{
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
 template <bool kGrad>
 __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
                                                             LossCfg cfg, float *__restrict__ grad,

@@ -6,4 +6,4 @@ from . import _lib
 from ._lib import YoloHotError, launch_count
 
 __version__ = "0.1.0"
-__all__ = ["utils", "loss", "metric", "dist", "YoloHotError", "launch_count"]
+__all__ = ["utils", "loss", "metric", "dataset", "dist", "YoloHotError", "launch_count"]

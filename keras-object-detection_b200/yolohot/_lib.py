@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libyolohot.so")
 
 YH_OK, YH_ERR_ARG, YH_ERR_CUDA, YH_ERR_UNSUPPORTED = 0, -1, -2, -4
+YH_DTYPE_F16, YH_DTYPE_BF16 = 1, 2
 
 _lib = None
 
@@ -19,6 +20,7 @@ SYMBOLS = (
     "yh_version", "yh_last_error", "yh_device_info", "yh_launch_count",
     "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_host", "yh_rows_append",
     "yh_loss", "yh_map_match", "yh_map_reduce",
+    "yh_encode_labels", "yh_head_to_f32", "yh_pixel_boxes",
     "yh_iou_dl", "yh_decode_dl", "yh_nms_dl", "yh_decode_nms_dl", "yh_loss_dl",
 )
 
@@ -51,6 +53,9 @@ def lib():
     L.yh_loss.argtypes = [vp, vp, i64, i, i, f, f, vp, vp, vp]
     L.yh_map_match.argtypes = [vp, i64, vp, i64, i, f, vp, vp, vp, vp]
     L.yh_map_reduce.argtypes = [vp, vp, i64, vp, i, vp, vp, vp]
+    L.yh_encode_labels.argtypes = [vp, vp, i64, i, i, i, vp, vp, vp]
+    L.yh_head_to_f32.argtypes = [vp, i, i64, vp, vp]
+    L.yh_pixel_boxes.argtypes = [vp, vp, i64, i, i, i, vp, vp]
     L.yh_iou_dl.argtypes = [vp, vp, vp, vp]
     L.yh_decode_dl.argtypes = [vp, i, i, vp, vp]
     L.yh_nms_dl.argtypes = [vp, f, f, vp, vp, vp, vp]

@@ -63,11 +63,42 @@ def as_device_f32(x, device=None):
     else:
         kind = "numpy"
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
-    if t.dtype != torch.float32:
-        t = t.to(torch.float32)          # the reference casts to float32 (utils.py:20-22, 91-92, 169-170)
     if not t.is_cuda:
         t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    if t.dtype in (torch.float16, torch.bfloat16):
+        t = head_to_f32(t)               # half-precision head output: exact widening kernel (yh_head_to_f32)
+    elif t.dtype != torch.float32:
+        t = t.to(torch.float32)          # the reference casts to float32 (utils.py:20-22, 91-92, 169-170)
     return t.contiguous(), kind
+
+
+def head_to_f32(t):
+    """fp16 / bf16 CUDA tensor -> float32 tensor of the same shape."""
+    from . import _lib
+    t = t.contiguous()
+    out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+    code = _lib.YH_DTYPE_F16 if t.dtype == torch.float16 else _lib.YH_DTYPE_BF16
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().yh_head_to_f32(t.data_ptr(), code, t.numel(), out.data_ptr(), stream_ptr(t.device)),
+                   "head_to_f32")
+    return out
+
+
+def as_grid(p, num_classes, num_boxes, grid=None):
+    """Head adapter (train.py:208 `tf.reshape(predictions, [-1, 7, 7, 30])`): a flat (N, S*S*D)
+    head output is viewed - zero-copy - as (N, S, S, D); 4-D input is checked and passed through.
+    Returns (tensor, N, S)."""
+    D = int(num_classes) + 5 * int(num_boxes)
+    if p.dim() == 2:
+        per = int(p.shape[1])
+        S = int(grid) if grid is not None else int(round((per / D) ** 0.5))
+        if S < 1 or S * S * D != per:
+            raise ValueError(f"flat head output of {per} values per image is not S*S*{D} for "
+                             f"{'grid=' + str(grid) if grid is not None else 'any square grid'}")
+        p = p.view(int(p.shape[0]), S, S, D)
+    if p.dim() != 4 or p.shape[1] != p.shape[2] or p.shape[3] != D or (grid is not None and int(p.shape[1]) != int(grid)):
+        raise ValueError(f"expected (N, S, S, {D}) or flat (N, S*S*{D}) predictions, got {tuple(p.shape)}")
+    return p, int(p.shape[0]), int(p.shape[1])
 
 
 def give_back(t, kind):

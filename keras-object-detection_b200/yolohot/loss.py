@@ -46,6 +46,8 @@ def yolo_v1_loss_terms(y_true, y_pred, num_classes=20, num_boxes=2, lambda_coord
     """[xy, wh, obj, noobj, cls, total] (loss.py:172-213) and optionally d(total)/d(y_pred)."""
     t, kind = as_device_f32(y_true)
     p, _ = as_device_f32(y_pred, t.device)
+    if p.dim() == 2 and t.dim() == 4 and p.numel() == t.numel():
+        p = p.view(t.shape)
     terms, g = _run(t, p, int(num_classes), int(num_boxes), lambda_coord, lambda_noobj, grad)
     if grad:
         return give_back(terms, kind), give_back(g, kind)
@@ -72,6 +74,8 @@ class YoloV1Loss:
             p = y_pred.contiguous()
         else:
             p, _ = as_device_f32(y_pred, t.device)
+        if p.dim() == 2 and t.dim() == 4 and p.numel() == t.numel():
+            p = p.view(t.shape)              # flat Dense head output (model.py:107; loss.py:122); autograd keeps the view
         self.batch_size = int(t.shape[0])                                   # loss.py:123
         total, terms = _LossFn.apply(t, p, int(self.num_classes), int(self.num_boxes),
                                      float(self.lambda_coord), float(self.lambda_noobj))

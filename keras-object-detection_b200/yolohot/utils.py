@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._tensor import DL, as_device_f32, dl, give_back, ptr, require_cuda, stream_ptr
+from ._tensor import DL, as_device_f32, as_grid, dl, give_back, ptr, require_cuda, stream_ptr
 
 __all__ = [
     "intersection_over_union", "intersection_over_union_numpy",
@@ -30,6 +30,7 @@ __all__ = [
     "decode_predictions", "decode_predictions_numpy", "get_all_bboxes", "decode_nms",
     "mean_average_precision", "mean_average_precision_numpy", "mean_average_precision_2",
     "MeanAveragePrecision", "MeanAveragePrecisionNumpy",
+    "pixel_boxes", "get_tagged_img", "get_grid_tagged_img",
 ]
 
 
@@ -56,17 +57,12 @@ def intersection_over_union_numpy(boxes1, boxes2):
 
 
 # ------------------------------------------------------------------------ decode
-def _grid_shape(p, num_classes, num_boxes):
-    if p.dim() != 4 or p.shape[1] != p.shape[2] or p.shape[3] != num_classes + 5 * num_boxes:
-        raise ValueError(f"expected (N, S, S, {num_classes + 5 * num_boxes}) predictions, got {tuple(p.shape)}")
-    return int(p.shape[0]), int(p.shape[1])
-
-
-def decode_predictions(predictions, num_classes, num_boxes=2):
+def decode_predictions(predictions, num_classes, num_boxes=2, grid=None):
     """utils.py:152-218: (N,S,S,C+5B) -> (N,S*S,6) rows [class_idx, confidence, cx, cy, w, h].
-    S is taken from the tensor (the reference hard-codes 7, utils.py:184,200-216)."""
+    S is taken from the tensor (the reference hard-codes 7, utils.py:184,200-216).  The flat
+    (N, S*S*(C+5B)) head output (model.py:107, reshaped at train.py:208) is accepted as it is."""
     p, kind = as_device_f32(predictions)
-    n, S = _grid_shape(p, num_classes, num_boxes)
+    p, n, S = as_grid(p, num_classes, num_boxes, grid)
     out = torch.empty((n, S * S, 6), dtype=torch.float32, device=p.device)
     with torch.cuda.device(p.device):
         hp, ho = DL(p), DL(out)
@@ -127,7 +123,7 @@ def non_max_suppression_2(boxes, iou_threshold=0.5, conf_threshold=0.4):
 
 
 def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_threshold=0.4,
-               return_index=False, out=None):
+               return_index=False, out=None, grid=None):
     """Fused, batched loop body of utils.py:470-480 (decode + per-image NMS).
 
     Returns (boxes (N,S*S,6), count (N,) int32[, keep_idx (N,S*S) int32]): the first count[i]
@@ -138,6 +134,11 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
     if not isinstance(predictions, torch.Tensor) and not hasattr(predictions, "__dlpack__") or isinstance(predictions, np.ndarray):
         require_cuda()
         p = np.ascontiguousarray(np.asarray(predictions, dtype=np.float32))
+        if p.ndim == 2:                                   # flat head output (train.py:208)
+            D_ = num_classes + 5 * num_boxes
+            S_ = int(grid) if grid is not None else int(round((p.shape[1] / D_) ** 0.5))
+            if S_ >= 1 and S_ * S_ * D_ == p.shape[1]:
+                p = p.reshape(p.shape[0], S_, S_, D_)
         if p.ndim != 4 or p.shape[1] != p.shape[2] or p.shape[3] != num_classes + 5 * num_boxes:
             raise ValueError(f"expected (N, S, S, {num_classes + 5 * num_boxes}) predictions, got {p.shape}")
         n, S = p.shape[0], p.shape[1]
@@ -150,7 +151,7 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
                    "decode_nms")
         return (boxes, cnt, kidx) if return_index else (boxes, cnt)
     p, kind = as_device_f32(predictions)
-    n, S = _grid_shape(p, num_classes, num_boxes)
+    p, n, S = as_grid(p, num_classes, num_boxes, grid)
     if out is not None:
         boxes, cnt = out[0], out[1]
         kidx = out[2] if (return_index and len(out) > 2) else None
@@ -288,7 +289,8 @@ class MeanAveragePrecision:
     def update_state(self, y_true, y_pred):
         yt, _ = as_device_f32(y_true)
         yp, _ = as_device_f32(y_pred, yt.device)
-        n, S = _grid_shape(yp, self._num_classes, self._num_boxes)
+        yp, n, S = as_grid(yp, self._num_classes, self._num_boxes)          # train.py:208: flat head output
+        yt, _, _ = as_grid(yt, self._num_classes, self._num_boxes)
         if tuple(yt.shape) != tuple(yp.shape):
             raise ValueError(f"update_state: y_true {tuple(yt.shape)} and y_pred {tuple(yp.shape)} differ")
         dev = yp.device
@@ -335,3 +337,67 @@ def _filter_rows(boxes, conf_threshold):
     order = torch.argsort(torch.where(kidx >= 0, kidx, torch.full_like(kidx, M)), dim=1, stable=True)
     out = torch.gather(out, 1, order.unsqueeze(-1).expand(-1, -1, 6)).contiguous()
     return out, cnt
+
+
+# ------------------------------------------------------------- drawing epilogue
+def pixel_boxes(boxes, width, height, count=None):
+    """utils.py:652-655: rows [cls, conf, cx, cy, w, h] -> int32 [xmin, ymin, xmax, ymax] with
+    xmin = int((cx - w/2) * width) etc. (float32, truncation).  boxes (K,6) -> (K,4); padded
+    (N,M,6) with `count` (N,) -> (N,M,4), rows past count[i] set to -1."""
+    b, kind = as_device_f32(boxes)
+    if b.dim() == 2 and b.shape[-1] == 6:
+        b3 = b.unsqueeze(0)
+    elif b.dim() == 3 and b.shape[-1] == 6:
+        b3 = b
+    else:
+        raise ValueError(f"pixel_boxes: expected (K, 6) or (N, M, 6) rows, got {tuple(b.shape)}")
+    n, M = int(b3.shape[0]), int(b3.shape[1])
+    out = torch.empty((n, M, 4), dtype=torch.int32, device=b.device)
+    cnt = None
+    if count is not None:
+        cnt = (count if isinstance(count, torch.Tensor) else torch.as_tensor(np.asarray(count)))
+        cnt = cnt.to(device=b.device, dtype=torch.int32).contiguous()
+        if cnt.numel() != n:
+            raise ValueError("pixel_boxes: count must hold one entry per image")
+    if n * M:
+        with torch.cuda.device(b.device):
+            _lib.check(_lib.lib().yh_pixel_boxes(b3.data_ptr(), cnt.data_ptr() if cnt is not None else None, n, M,
+                                                 int(width), int(height), out.data_ptr(), stream_ptr(b.device)),
+                       "pixel_boxes")
+    out = out[0] if b.dim() == 2 else out
+    return out.cpu().numpy() if kind == "numpy" else out
+
+
+def _draw(img, boxes, names_path, with_grid):
+    import cv2                                   # host-side drawing, exactly the reference's calls
+    b, _ = as_device_f32(boxes)
+    b = b.reshape(-1, 6)
+    height, width = img.shape[0], img.shape[1]
+    with open(names_path, "r") as f:
+        class_name_list = [x.strip() for x in f.readlines()]
+    px = pixel_boxes(b, width, height).cpu().numpy()
+    rows = b.cpu().numpy()
+    for row, (xmin, ymin, xmax, ymax) in zip(rows, px.tolist()):
+        class_name = class_name_list[int(row[0])]
+        img = cv2.rectangle(img, (xmin, ymin), (xmax, ymax), color=(0, 255, 0))
+        if with_grid:                                                                    # utils.py:701
+            img = cv2.circle(img, (int(row[2] * np.float32(width)), int(row[3] * np.float32(height))), radius=2,
+                             color=(0, 0, 255))
+        img = cv2.putText(img, "{:s}, {:.2f}".format(class_name, row[1]), (xmin, ymin + 20),
+                          fontFace=cv2.FONT_HERSHEY_PLAIN, fontScale=1, color=(0, 255, 0))
+    if with_grid:                                                                        # utils.py:708-711
+        for idx in range(6):
+            a = int(448 * ((idx + 1) / 7.))
+            img = cv2.line(img, (a, 0), (a, height), color=(255, 0, 255))
+            img = cv2.line(img, (0, a), (width, a), color=(255, 0, 255))
+    return img
+
+
+def get_tagged_img(img, boxes, names_path):
+    """utils.py:623-663: draw the kept boxes; corner arithmetic on the device (yh_pixel_boxes)."""
+    return _draw(img, boxes, names_path, False)
+
+
+def get_grid_tagged_img(img, boxes, names_path):
+    """utils.py:666-713: same plus box centres and the 7x7 grid lines."""
+    return _draw(img, boxes, names_path, True)

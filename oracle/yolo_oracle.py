@@ -416,3 +416,24 @@ def encode_labels(boxes, grid, num_classes, num_boxes):
             m[li, lj, C + 1:C + 5] = [x, y, w, h]
             m[li, lj, C] = 1
     return m
+
+
+def encode_labels_batch(boxes, offsets, grid, num_classes, num_boxes):
+    """dataset.py:72-86 label half: (total,5) float64 rows + (N+1) offsets -> (N,S,S,C+5B) float32
+    (each image's float64 grid is assigned into the float32 batch array, dataset.py:85)."""
+    n = len(offsets) - 1
+    out = np.zeros((n, grid, grid, num_classes + 5 * num_boxes), F32)
+    for i in range(n):
+        out[i] = encode_labels(np.asarray(boxes, np.float64)[offsets[i]:offsets[i + 1]], grid, num_classes, num_boxes)
+    return out
+
+
+def pixel_boxes(rows, width, height):
+    """utils.py:652-655 on float32 values: xmin = int((x - (w / 2)) * width) ...; int() truncates."""
+    r = np.asarray(rows, F32).reshape(-1, 6)
+    out = np.zeros((len(r), 4), np.int32)
+    for i, box in enumerate(r):
+        x, y, w, h = box[2], box[3], box[4], box[5]
+        out[i] = [int((x - (w / 2)) * width), int((y - (h / 2)) * height),
+                  int((x + (w / 2)) * width), int((y + (h / 2)) * height)]
+    return out

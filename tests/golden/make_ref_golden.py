@@ -28,6 +28,15 @@ import tensorflow as tf  # noqa: E402  (the stand-in)
 import torch  # noqa: E402
 
 assert "numpy-standin" in tf.__version__
+import types  # noqa: E402
+
+# dataset.py:7-9 imports its augmentation libraries at module level; none is used by the label
+# code that is executed here (_get_boxes / _get_labels), so empty modules stand in for them
+for _name in ("imgaug", "imgaug.augmenters", "albumentations"):
+    sys.modules.setdefault(_name, types.ModuleType(_name))
+sys.modules["imgaug"].augmenters = sys.modules["imgaug.augmenters"]
+
+import dataset as RD  # noqa: E402  /root/reference/yolo_v1/dataset.py
 import loss as RL  # noqa: E402   /root/reference/yolo_v1/loss.py
 import utils as RU  # noqa: E402  /root/reference/yolo_v1/utils.py
 
@@ -60,6 +69,45 @@ def evaluator(batches, C, B):
         ev.update_state(T(yt), T(yp))
     m = np.float32(np.asarray(ev.result()))
     return m, np.asarray(ev.all_true_boxes_variable), np.asarray(ev.all_pred_boxes_variable)
+
+
+def label_generator(grid, C, B):
+    """A YoloV1Generator (dataset.py:19) without its image directory: only what _get_labels reads."""
+    gen = RD.YoloV1Generator.__new__(RD.YoloV1Generator)
+    gen.grid, gen.num_classes, gen.num_boxes = grid, C, B
+    gen.output_shape = (grid, grid, C + B * 5)
+    return gen
+
+
+def labels_of(gen, box_lists):
+    """dataset.py:72-86: batch_labels is float32, each image assigned from _get_labels' float64 grid."""
+    out = np.zeros((len(box_lists),) + gen.output_shape, dtype=F32)
+    for i, b in enumerate(box_lists):
+        out[i] = gen._get_labels(b)
+    return out
+
+
+def flat(box_lists):
+    offs = np.zeros(len(box_lists) + 1, np.int64)
+    offs[1:] = np.cumsum([len(b) for b in box_lists])
+    rows = [np.asarray(b, np.float64).reshape(-1, 5) for b in box_lists]
+    return (np.concatenate(rows, 0) if rows else np.zeros((0, 5))), offs
+
+
+def recorded_pixel_boxes(fn, img_shape, boxes, names_path):
+    """Runs utils.get_tagged_img / get_grid_tagged_img and records the corners handed to cv2.rectangle."""
+    rec = []
+    real = RU.cv2.rectangle
+
+    def spy(img, p0, p1, **kw):
+        rec.append([p0[0], p0[1], p1[0], p1[1]])
+        return real(img, p0, p1, **kw)
+    RU.cv2.rectangle = spy
+    try:
+        fn(np.zeros(img_shape, np.uint8), T(boxes), names_path)
+    finally:
+        RU.cv2.rectangle = real
+    return np.array(rec, np.int32).reshape(-1, 4)
 
 
 def main():
@@ -134,6 +182,49 @@ def main():
     g["rows_true"], g["rows_pred"] = true_rows, pred_rows
     g["rows_map"] = np.float32(np.asarray(RU.mean_average_precision(T(true_rows), T(pred_rows), 4)))
     g["rows_map_thr03"] = np.float32(np.asarray(RU.mean_average_precision(T(true_rows), T(pred_rows), 4, iou_threshold=0.3)))
+
+    # ---- N2: label grids (dataset.py:88-123) ------------------------------------------------
+    gen = label_generator(7, 3, 2)
+    txt = gen._get_boxes(os.path.join(REF, "data", "test.txt"))          # the reference's own label file
+    g["lab_txt_boxes"] = np.asarray(txt, np.float64)
+    g["lab_txt_out"] = labels_of(gen, [txt])
+    rng = np.random.Generator(np.random.PCG64(21))
+    lists = []
+    for i in range(24):
+        k = int(rng.integers(0, 12)) if i != 3 else 70               # an empty image, and one with > 64 boxes
+        b = np.concatenate([rng.random((k, 2)), 0.05 + 0.9 * rng.random((k, 2)), rng.integers(0, 20, (k, 1))], 1)
+        if k >= 4:
+            b[1, :2] = b[0, :2] + 0.001                                # two boxes in one cell: first one wins (:107)
+            b[2, 0], b[2, 1] = 3.0 / 7.0, 5.0 / 7.0                    # centres on cell boundaries
+            b[3, 0], b[3, 1] = -0.05, 0.999999                         # int() truncates toward zero; x < 0
+        if i == 5 and k:
+            b[0, 4] = -1                                               # Python index wrap: channel D-1
+            b[0, 0] = -0.2                                             # cell index -1 -> last column
+        lists.append(b)
+    gen = label_generator(7, 20, 2)
+    g["lab_boxes"], g["lab_offsets"] = flat(lists)
+    g["lab_out"] = labels_of(gen, lists)
+    lists3 = [np.concatenate([rng.random((6, 2)), 0.1 + 0.5 * rng.random((6, 2)), rng.integers(0, 80, (6, 1))], 1)
+              for _ in range(5)]
+    gen = label_generator(14, 80, 3)
+    g["lab14_boxes"], g["lab14_offsets"] = flat(lists3)
+    g["lab14_out"] = labels_of(gen, lists3)
+    try:                                                                 # cx = 1.0 -> cell index 7
+        label_generator(7, 20, 2)._get_labels(np.array([[1.0, 0.5, 0.1, 0.1, 0]]))
+        g["lab_out_of_grid_raises"] = np.array(0)
+    except IndexError:
+        g["lab_out_of_grid_raises"] = np.array(1)
+
+    # ---- N4: pixel corners handed to cv2.rectangle (utils.py:645-657, 688-700) ---------------
+    names = os.path.join(REF, "data", "test.names")
+    rows = np.concatenate([g["demo_nms_pred"], g["demo_nms_true"]], 0)
+    extra = rng.random((40, 6), dtype=F32)
+    extra[:, 0] = rng.integers(0, 3, 40)
+    extra[:, 4:] *= F32(1.5)                                            # some corners fall outside the image
+    rows = np.concatenate([rows, extra], 0).astype(F32)
+    g["px_rows"] = rows
+    g["px_448"] = recorded_pixel_boxes(RU.get_tagged_img, (448, 448, 3), rows, names)
+    g["px_375x500"] = recorded_pixel_boxes(RU.get_grid_tagged_img, (375, 500, 3), rows, names)
 
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "ref_golden.npz")
     np.savez_compressed(out, **g)

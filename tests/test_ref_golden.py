@@ -81,6 +81,20 @@ def test_oracle_map_matches_reference_source():
         assert abs(float(got) - float(R[key])) <= 1e-6, (key, got, R[key])
 
 
+def test_oracle_label_grids_match_reference_source():
+    assert np.array_equal(O.encode_labels_batch(R["lab_txt_boxes"], [0, 3], 7, 3, 2), R["lab_txt_out"])
+    assert np.array_equal(O.encode_labels_batch(R["lab_boxes"], R["lab_offsets"], 7, 20, 2), R["lab_out"])
+    assert np.array_equal(O.encode_labels_batch(R["lab14_boxes"], R["lab14_offsets"], 14, 80, 3), R["lab14_out"])
+    assert int(R["lab_out_of_grid_raises"]) == 1
+    with pytest.raises(IndexError):
+        O.encode_labels(np.array([[1.0, 0.5, 0.1, 0.1, 0]]), 7, 20, 2)
+
+
+def test_oracle_pixel_boxes_match_reference_source():
+    assert np.array_equal(O.pixel_boxes(R["px_rows"], 448, 448), R["px_448"])
+    assert np.array_equal(O.pixel_boxes(R["px_rows"], 500, 375), R["px_375x500"])
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/yolo_v1"), reason="reference sources only exist in the build container")
 def test_committed_golden_is_what_the_reference_source_returns(tmp_path):
     """Re-executes the reference's files (make_ref_golden.py) and compares with the committed file."""
@@ -169,3 +183,62 @@ def test_cuda_map_matches_reference_source(dev):
     for key, thr in (("rows_map", 0.5), ("rows_map_thr03", 0.3)):
         got = yu.mean_average_precision(_cuda(R["rows_true"], dev), _cuda(R["rows_pred"], dev), 4, thr)
         assert abs(float(got) - float(R[key])) <= 1e-6, (key, float(got), R[key])
+
+
+@pytest.mark.gpu
+def test_cuda_label_grids_match_reference_source(dev):
+    from yolohot import dataset as yd
+    for key, S, C, B in (("lab", 7, 20, 2), ("lab14", 14, 80, 3)):
+        out = yd.encode_labels(R[f"{key}_boxes"], R[f"{key}_offsets"], S, C, B, device=dev)
+        assert out.dtype == torch.float32 and np.array_equal(out.cpu().numpy(), R[f"{key}_out"]), key
+    # list-of-lists form, the reference's own label file, and the generator-shaped class
+    lists = [R["lab_boxes"][a:b] for a, b in zip(R["lab_offsets"][:-1], R["lab_offsets"][1:])]
+    assert np.array_equal(yd.encode_labels(lists, None, 7, 20, 2, device=dev).cpu().numpy(), R["lab_out"])
+    gen = yd.YoloV1Labels(3, 2)
+    assert np.array_equal(gen._get_labels(R["lab_txt_boxes"]).cpu().numpy(), R["lab_txt_out"][0])
+    with pytest.raises(IndexError):                       # dataset.py:107 raises for cx = 1.0
+        yd.get_labels(np.array([[1.0, 0.5, 0.1, 0.1, 0]]), 7, 20, 2)
+    # the labels feed the evaluator: decode + NMS of the encoded grid returns the boxes
+    rows, cnt = __import__("yolohot.utils", fromlist=["x"]).decode_nms(gen.batch([R["lab_txt_boxes"]]), 3, 2)
+    assert int(cnt[0]) == 3
+
+
+@pytest.mark.gpu
+def test_cuda_pixel_boxes_match_reference_source(dev):
+    from yolohot import utils as yu
+    rows = _cuda(R["px_rows"], dev)
+    assert np.array_equal(yu.pixel_boxes(rows, 448, 448).cpu().numpy(), R["px_448"])
+    assert np.array_equal(yu.pixel_boxes(rows, 500, 375).cpu().numpy(), R["px_375x500"])
+    padded = torch.zeros((2, 46, 6), device=dev)
+    padded[0] = rows
+    padded[1, :5] = rows[:5]
+    px = yu.pixel_boxes(padded, 448, 448, count=torch.tensor([46, 5])).cpu().numpy()
+    assert np.array_equal(px[0], R["px_448"]) and np.array_equal(px[1, :5], R["px_448"][:5]) and (px[1, 5:] == -1).all()
+
+
+@pytest.mark.gpu
+def test_cuda_head_adapter(dev):
+    """train.py:208: the flat Dense output is the same memory as (N,7,7,30); half heads widen exactly."""
+    from yolohot import loss as yloss, utils as yu
+    p = R["dense_in"]
+    flat = _cuda(p.reshape(p.shape[0], -1), dev)
+    rows, cnt = yu.decode_nms(flat, 20, 2)
+    assert np.array_equal(cnt.cpu().numpy(), R["dense_count"])
+    assert np.array_equal(_kept(rows.cpu().numpy(), cnt.cpu().numpy()), _kept(R["dense_rows"], R["dense_count"]))
+    assert np.array_equal(yu.decode_predictions(flat, 20, 2).cpu().numpy(), R["dense_decode"])
+    with pytest.raises(ValueError):
+        yu.decode_nms(flat[:, :-1].contiguous(), 20, 2)
+    for dt in (torch.float16, torch.bfloat16):
+        h = _cuda(p, dev).to(dt)
+        want = yu.decode_nms(h.float(), 20, 2)
+        got = yu.decode_nms(h, 20, 2)
+        assert torch.equal(got[1], want[1])
+        m = torch.arange(49, device=dev)[None, :] < want[1][:, None]
+        assert torch.equal(got[0][m], want[0][m])
+    yt = _cuda(R["loss16_yt"], dev)
+    yp = _cuda(R["loss16_yp"].reshape(16, -1), dev).requires_grad_(True)
+    tot = yloss.YoloV1Loss(20, 2)(yt, yp)
+    tot.backward()
+    assert abs(float(tot.detach()) - float(R["loss16_total"])) <= 1e-5 * abs(float(R["loss16_total"]))
+    np.testing.assert_allclose(yp.grad.cpu().numpy().reshape(R["loss16_grad_torch"].shape), R["loss16_grad_torch"],
+                               rtol=1e-4, atol=1e-4)
