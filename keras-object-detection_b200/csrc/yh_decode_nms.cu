@@ -19,6 +19,7 @@
 // mbarrier ring filled by a producer warp; a direct-from-global kernel covers the tail,
 // unaligned inputs and grids too large for the ring.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "yh_common.cuh"
@@ -29,6 +30,7 @@ struct NmsCfg {
     int S, B, C, M, D;       // grid, boxes, classes, cells = S*S, channels = C + 5B
     float inv_s;             // float32(1 / S)                         (utils.py:207)
     float iou_thr, conf_thr;
+    int thr_fast;            // iou_thr is a positive normal float: the division-free filter of suppresses() applies
     int ws_bytes;            // per-warp workspace bytes
     int tbl_rows;            // rows of the class table (C for fused, 32*NS for row input)
     int stage_bytes;         // direct kernel: per-warp staging buffer for one slot (32 cells), 0 = none
@@ -50,6 +52,20 @@ struct WarpWs {
     int *outpos;      //          aliased afterwards: output slot of rank position q, -1 = suppressed
     float *cclsf;     // [MP]  compact float classes          (kFloatCls only)
     unsigned *tbl;    // [tbl_rows * NS] class key -> lanes holding that class, per slot
+    unsigned *supp_s; // [MP * NS] suppression bit rows in shared memory (pair-parallel phase D), else nullptr
+    unsigned char *list;   // [MP]  rank positions of the members of one class, in rank order
+
+    // Bit rows are triangular: rank position q = lane + 32 t only has predecessors in words 0..t, so
+    // its row holds t + 1 words; rows of slot t start at word 32 * t(t+1)/2.
+    static constexpr int kSuppWords = 16 * NS * (NS + 1);
+    __host__ __device__ static int supp_row(int q) { const int t = q >> 5; return 16 * t * (t + 1) + (q & 31) * (t + 1); }
+    // extra bytes behind bytes(tbl_rows) when the pair-parallel phase D is used
+    __host__ __device__ static int pair_bytes() { return kSuppWords * 4 + MP; }
+    __device__ void enable_pairs(unsigned char *p)
+    {
+        supp_s = reinterpret_cast<unsigned *>(p);
+        list = p + kSuppWords * 4;
+    }
 
     __host__ __device__ static int bytes(int tbl_rows)
     {
@@ -70,21 +86,35 @@ struct WarpWs {
             cclsf = reinterpret_cast<float *>(p);  p += MP * 4;
         }
         tbl = reinterpret_cast<unsigned *>(p);
+        supp_s = nullptr;
+        list = nullptr;
     }
 };
 
 // IoU test of the reference from precomputed corners/areas: p = chosen (earlier) box, q = later
 // box.  Same float32 operations in the same order as utils.py:34-43 (min/max/+ commute bit for
-// bit), so the decision is the reference's.  A zero intersection gives IoU = +0 exactly
-// (denominator >= 1e-6 > 0): skip the IEEE division, whose zero-numerator case is a slow path.
-__device__ __forceinline__ bool suppresses(const float4 &pc, float pa, const float4 &qc, float qa, float iou_thr)
+// bit), so the decision is the reference's: suppress iff !(fl32(inter / den) < thr) (utils.py:108).
+//
+// The IEEE division (a ~16-instruction sequence with a slow path) is almost never evaluated.  With
+// p = fl(thr * den) and d = fl(inter - p) (den > 0, thr > 0): |d| > 2^-20 p implies that inter / den
+// differs from thr by more than a relative 2^-21 (p carries a relative error <= 2^-24 and the
+// subtraction is correctly rounded, so its sign and size are right), which is far outside the
+// rounding interval of the quotient (relative 2^-24 around thr): the sign of d decides exactly like
+// fl(inter / den) < thr.  Inside the band (probability ~1e-6 per test on continuous data), for
+// den <= 0 (degenerate negative-extent boxes), NaN/inf operands or an unusual thr, the reference's
+// own division decides.
+__device__ __forceinline__ bool suppresses(const float4 &pc, float pa, const float4 &qc, float qa, const NmsCfg &cfg)
 {
     const float iw = clip01(__fsub_rn(fminf(pc.y, qc.y), fmaxf(pc.x, qc.x)));
     const float ih = clip01(__fsub_rn(fminf(pc.w, qc.w), fmaxf(pc.z, qc.z)));
     const float inter = __fmul_rn(iw, ih);
-    float v = 0.0f;
-    if (inter != 0.0f) v = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(pa, qa), inter), 1e-6f));
-    return !(v < iou_thr);                                   // utils.py:108 keeps iff iou < thr
+    const float den = __fadd_rn(__fsub_rn(__fadd_rn(pa, qa), inter), 1e-6f);
+    const float p = __fmul_rn(cfg.iou_thr, den);
+    const float d = __fsub_rn(inter, p);
+    if (cfg.thr_fast && den > 0.0f && fabsf(d) > __fmul_rn(p, 9.5367431640625e-07f)) return !(d < 0.0f);
+    float v = 0.0f;                                          // a zero intersection gives IoU = +0 exactly
+    if (inter != 0.0f) v = __fdiv_rn(inter, den);
+    return !(v < cfg.iou_thr);                               // utils.py:108 keeps iff iou < thr
 }
 
 // ------------------------------------------------------------------------------------------
@@ -256,10 +286,116 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
             const unsigned w = lo ? cur_lo : cur_hi;
             const unsigned bit = w & (0u - w);
             const int p = (31 - __clz(bit)) + (lo ? 0 : 32);
-            const unsigned sb = suppresses(ws.scor[p], ws.sarea[p], qc, qa, cfg.iou_thr) ? bit : 0u;
+            const unsigned sb = suppresses(ws.scor[p], ws.sarea[p], qc, qa, cfg) ? bit : 0u;
             if (lo) { cur_lo ^= bit; s_lo |= sb; } else { cur_hi ^= bit; s_hi |= sb; }
         }
         if (on1) { supp[1][0] = s_lo; supp[1][1] = s_hi; } else { supp[0][0] = s_lo; }
+    } else if (ws.supp_s != nullptr) {
+        // Pair-parallel phase D.  With lane = candidate, a warp runs max-over-lanes trips and most
+        // lanes idle (few candidates have many same-class predecessors).  Instead, every class with
+        // more than kSmall members is processed on its own: its members are listed in rank order and
+        // the k(k-1)/2 (earlier, later) pairs are dealt out to the 32 lanes, one IoU test per lane
+        // and step, hits OR-ed into the later box's bit row in shared memory.  Small classes keep
+        // the lane = candidate loop (at most kSmall - 1 tests per candidate).
+        constexpr int kSmall = 5;
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(ws.supp_s);
+            const int nz = (16 * NT * (NT + 1) + 3) >> 2;          // rows of slots 0..NT-1
+            for (int i = lane; i < nz; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        int jq[NS], kq[NS];                        // index within the class (rank order) / class size
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            jq[t] = 0; kq[t] = 0;
+            if (t < NT && ((act_m >> t) & 1u)) {
+                const unsigned *row = ws.tbl + qkey[t] * NS;
+#pragma unroll
+                for (int t2 = 0; t2 < NS; ++t2) {
+                    if (t2 < NT) {
+                        const unsigned w = row[t2];
+                        kq[t] += __popc(w);
+                        if (t2 < t) jq[t] += __popc(w);
+                        if (t2 == t) jq[t] += __popc(w & lt_mask);
+                    }
+                }
+            }
+        }
+        __syncwarp();                              // rows are zeroed before anybody ORs into them
+        // small classes: lane = candidate
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            if (t < NT && ((act_m >> t) & 1u) && kq[t] <= kSmall && jq[t] > 0) {
+                const unsigned *row = ws.tbl + qkey[t] * NS;
+                const int q = lane + 32 * t;
+                const float4 qc = ws.scor[q];
+                const float qa = ws.sarea[q];
+                for (int t2 = 0; t2 <= t; ++t2) {
+                    unsigned w = row[t2];
+                    if (t2 == t) w &= lt_mask;
+                    unsigned acc = 0u;
+                    while (w) {
+                        const int b = __ffs(w) - 1;
+                        w &= w - 1;
+                        if (suppresses(ws.scor[32 * t2 + b], ws.sarea[32 * t2 + b], qc, qa, cfg)) acc |= 1u << b;
+                    }
+                    if (acc) ws.supp_s[ws.supp_row(q) + t2] = acc;
+                }
+            }
+        }
+        // big classes, one after the other (warp-uniform loop over their first members)
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            if (t >= NT) continue;
+            unsigned bm = __ballot_sync(FULL, ((act_m >> t) & 1u) && jq[t] == 0 && kq[t] > kSmall);
+            while (bm) {
+                const int src = __ffs(bm) - 1;
+                bm &= bm - 1;
+                const int key_c = __shfl_sync(FULL, qkey[t], src);
+                const int k = __shfl_sync(FULL, kq[t], src);
+#pragma unroll
+                for (int u = 0; u < NS; ++u)
+                    if (u < NT && ((act_m >> u) & 1u) && qkey[u] == key_c) ws.list[jq[u]] = static_cast<unsigned char>(lane + 32 * u);
+                __syncwarp();
+                // The k(k-1)/2 pairs as a folded triangle: virtual row v joins the predecessors of member
+                // k-1-v (x < k-1-v) with those of member v, k-1 entries in all; pair e sits at row
+                // e / (k-1), column e % (k-1) - closed form, every lane busy, two pairs per trip so that
+                // two independent load -> test chains are in flight.
+                const int P = (k * (k - 1)) >> 1;
+                const int km1 = k - 1;
+                const float inv = 1.0f / static_cast<float>(km1);
+                auto pair_of = [&](int e, int &a, int &b) {
+                    int v = static_cast<int>(static_cast<float>(e) * inv);     // e < 2^15: off by at most one
+                    int x = e - v * km1;
+                    if (x < 0) { x += km1; --v; }
+                    if (x >= km1) { x -= km1; ++v; }
+                    const int b1 = km1 - v;
+                    const bool first = x < b1;
+                    b = first ? b1 : v;
+                    a = first ? x : x - b1;
+                };
+                for (int e = lane; e < P; e += 64) {
+                    const bool two = (e + 32) < P;
+                    int a, b, a2, b2;
+                    pair_of(e, a, b);
+                    pair_of(two ? e + 32 : e, a2, b2);
+                    const int pa = ws.list[a], pb = ws.list[b];
+                    const int pa2 = ws.list[a2], pb2 = ws.list[b2];
+                    const bool s1 = suppresses(ws.scor[pa], ws.sarea[pa], ws.scor[pb], ws.sarea[pb], cfg);
+                    const bool s2 = suppresses(ws.scor[pa2], ws.sarea[pa2], ws.scor[pb2], ws.sarea[pb2], cfg);
+                    if (s1) atomicOr(ws.supp_s + ws.supp_row(pb) + (pa >> 5), 1u << (pa & 31));
+                    if (s2 && two) atomicOr(ws.supp_s + ws.supp_row(pb2) + (pa2 >> 5), 1u << (pa2 & 31));
+                }
+                __syncwarp();                      // the list is rewritten by the next class
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            if (t < NT && ((act_m >> t) & 1u)) {
+#pragma unroll
+                for (int t2 = 0; t2 <= t; ++t2) supp[t][t2] = ws.supp_s[16 * t * (t + 1) + lane * (t + 1) + t2];
+            }
+        }
     } else {
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
@@ -274,7 +410,7 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
                     while (w) {
                         const int b = __ffs(w) - 1;
                         w &= w - 1;
-                        if (suppresses(ws.scor[32 * t2 + b], ws.sarea[32 * t2 + b], qc, qa, cfg.iou_thr)) supp[t][t2] |= 1u << b;
+                        if (suppresses(ws.scor[32 * t2 + b], ws.sarea[32 * t2 + b], qc, qa, cfg)) supp[t][t2] |= 1u << b;
                     }
                 }
             }
@@ -362,6 +498,39 @@ __device__ __forceinline__ void decode_cell(const float *__restrict__ p, const N
                 bw = v[CT + 5 * b + 3]; bh = v[CT + 5 * b + 4];
             }
         }
+    } else if constexpr (CT > 0 && BT > 0) {
+        // odd channel count (rows are only 4-byte aligned): scalar loads with immediate offsets.
+        // Class argmax in blocks of 8: block maximum (one FMNMX per score), the FIRST block whose
+        // maximum beats the running one (strict >, so ties stay with the earlier block), then the
+        // first score of that block equal to the maximum = tf.argmax's first maximum (utils.py:173).
+        constexpr int NB = (CT + 7) / 8;
+        float best = 0.f;
+        int bb = 0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float m = p[8 * b];
+#pragma unroll
+            for (int i = 1; i < 8; ++i)
+                if (8 * b + i < CT) m = fmaxf(m, p[8 * b + i]);
+            if (b == 0) best = m;
+            else if (m > best) { best = m; bb = b; }
+        }
+        cls = 8 * bb;
+#pragma unroll
+        for (int i = 7; i >= 1; --i) {
+            const int j = min(8 * bb + i, CT - 1);
+            if (p[j] == best) cls = j;
+        }
+        if (p[8 * bb] == best) cls = 8 * bb;
+        int k = 0;
+        conf = p[CT];
+#pragma unroll
+        for (int b = 1; b < BT; ++b) {
+            const float x = p[CT + 5 * b];
+            if (x > conf) { conf = x; k = b; }                    // first max over boxes (utils.py:183)
+        }
+        const float *q = p + CT + 5 * k;
+        bx = q[1]; by = q[2]; bw = q[3]; bh = q[4];
     } else {
         const int C = cfg.C, B = cfg.B;
         cls = 0;
@@ -639,6 +808,166 @@ __global__ void __launch_bounds__(800, 1) decode_nms_tma_kernel(const float *__r
 }
 
 // ------------------------------------------------------------------------------------------
+// Big-image kernel (images > 12 KB, e.g. S=14, B=3, C=80: 74,480 B): persistent CTAs, three warp
+// roles connected by mbarrier queues, so that no warp ever waits on global-memory latency:
+//   warp 0            producer: cp.async.bulk (TMA) of 32-cell chunks (32*D*4 B) of the CTA's images,
+//                     in order, into an ST-deep shared-memory ring
+//   warps 1..ND       decode warps: chunk c of the CTA's flat chunk sequence goes to warp c % ND; lane
+//                     = cell; the decoded (conf, class, box) of the cell is written to the input area
+//                     of the NMS warp that owns the image, then the ring stage is released
+//   warps ND+1..      NMS warps: image i of the CTA goes to warp i % NN; it pulls the decoded image
+//                     into registers, frees its input area for the next image and runs phases B..F
+// Queues: full/empty per ring stage; in_full (count = chunks per image) / in_empty per NMS warp.
+// mbarrier parity waits are only meaningful while the waiter is within one phase of the barrier,
+// which the host configuration guarantees: ST is a multiple of ND, so a stage (c % ST) is always
+// consumed by the same decode warp (c % ND) and that warp's waits on it are strictly sequential; ND
+// <= chunks per image, so every decode warp holds a chunk of every image and none can run a whole
+// round ahead of an NMS warp's input area; in_full[w] is only waited on by NMS warp w.
+// ------------------------------------------------------------------------------------------
+struct BigCfg {
+    int ST, ND, NN;         // ring stages, decode warps, NMS warps
+    int slots;              // chunks per image = ceil(M / 32)
+    uint32_t chunk_bytes;   // 32 * D * 4
+    uint32_t last_bytes;    // bytes of the last chunk of an image
+    int in_bytes;           // per NMS warp: decoded image area (conf, cls, box per cell)
+    int pairs, pair_bytes;  // pair-parallel phase D (NS > 2): extra per-NMS-warp bytes (bit rows + class list)
+    int64_t n;
+};
+
+template <int NS, int CT, int BT>
+__global__ void __launch_bounds__(512, 1) decode_nms_big_kernel(const float *__restrict__ pred, NmsCfg cfg, BigCfg bc,
+                                                                float *__restrict__ out_boxes, int *__restrict__ out_count,
+                                                                int *__restrict__ out_idx)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int MP = 32 * NS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *ring = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(bc.ST) * bc.chunk_bytes);
+    uint64_t *empty = full + bc.ST;
+    uint64_t *in_full = empty + bc.ST;
+    uint64_t *in_empty = in_full + bc.NN;
+    unsigned char *areas = reinterpret_cast<unsigned char *>(in_empty + bc.NN);
+    areas += (16 - (reinterpret_cast<uintptr_t>(areas) & 15)) & 15;
+    const int per_nms = cfg.ws_bytes + bc.in_bytes + bc.pair_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < bc.ST; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        for (int w = 0; w < bc.NN; ++w) {
+            mbar_init(in_full + w, bc.slots);
+            mbar_init(in_empty + w, 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // images of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int64_t my_imgs = (bc.n > blockIdx.x) ? (bc.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_chunks = my_imgs * bc.slots;
+    const int64_t img_bytes = 4ll * cfg.M * cfg.D;
+
+    if (warp == 0) {                                               // ---- producer
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(pred);
+            int s = 0, t = 0;
+            uint32_t ph = 0;
+            int64_t i = 0;
+            for (int64_t c = 0; c < n_chunks; ++c) {
+                mbar_wait_relaxed(empty + s, ph ^ 1u, 128);
+                const uint32_t bytes = (t == bc.slots - 1) ? bc.last_bytes : bc.chunk_bytes;
+                mbar_arrive_expect_tx(full + s, bytes);
+                bulk_g2s(ring + static_cast<size_t>(s) * bc.chunk_bytes,
+                         src + (blockIdx.x + i * gridDim.x) * img_bytes + static_cast<size_t>(t) * bc.chunk_bytes, bytes,
+                         full + s, pol);
+                if (++s == bc.ST) { s = 0; ph ^= 1u; }
+                if (++t == bc.slots) { t = 0; ++i; }
+            }
+        }
+        return;
+    }
+    if (warp <= bc.ND) {                                           // ---- decode warps
+        const int d = warp - 1;
+        // chunk c = d, d + ND, ...: image i = c / slots, slot t = c % slots, stage s = c % ST and its
+        // phase, NMS warp w = i % NN and its round - all kept incrementally
+        int64_t i = d / bc.slots;
+        int t = d % bc.slots, s = d % bc.ST, w = static_cast<int>(i % bc.NN);
+        uint32_t ph = static_cast<uint32_t>((d / bc.ST) & 1), r = static_cast<uint32_t>((i / bc.NN) & 1);
+        const int di = bc.ND / bc.slots, dt = bc.ND % bc.slots;        // step of (i, t) per chunk stride
+        for (int64_t c = d; c < n_chunks; c += bc.ND) {
+            const int cell = 32 * t + lane;
+            const bool valid = cell < cfg.M;
+            const int row = cell / cfg.S, col = cell - row * cfg.S;
+            int cls = 0;
+            float conf = -INFINITY;
+            float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+            mbar_wait(full + s, ph);
+            if (valid)
+                decode_cell<CT, BT>(reinterpret_cast<const float *>(ring + static_cast<size_t>(s) * bc.chunk_bytes) + lane * cfg.D,
+                                    cfg, static_cast<float>(col), static_cast<float>(row), cls, conf, box);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);                 // chunk is in registers: hand the stage back
+            mbar_wait(in_empty + w, r ^ 1u);                       // the NMS warp has taken its previous image
+            unsigned char *in = areas + static_cast<size_t>(w) * per_nms + cfg.ws_bytes;
+            if (valid) {
+                reinterpret_cast<float4 *>(in)[cell] = box;
+                reinterpret_cast<float *>(in + MP * 16)[cell] = conf;
+                reinterpret_cast<int *>(in + MP * 20)[cell] = cls;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(in_full + w);
+            // advance to chunk c + ND
+            s += bc.ND;                                            // ST is a multiple of ND: one wrap at most
+            if (s >= bc.ST) { s -= bc.ST; ph ^= 1u; }
+            int wi = di;
+            t += dt;
+            if (t >= bc.slots) { t -= bc.slots; ++wi; }
+            i += wi;
+            w += wi;
+            while (w >= bc.NN) { w -= bc.NN; r ^= 1u; }
+        }
+        return;
+    }
+    // ---- NMS warps
+    const int w = warp - 1 - bc.ND;
+    if (w >= bc.NN) return;
+    WarpWs<NS, false> ws(areas + static_cast<size_t>(w) * per_nms);
+    const unsigned char *in = areas + static_cast<size_t>(w) * per_nms + cfg.ws_bytes;
+    if (bc.pairs) ws.enable_pairs(areas + static_cast<size_t>(w) * per_nms + cfg.ws_bytes + bc.in_bytes);
+    for (int i = lane; i < cfg.tbl_rows * NS; i += 32) ws.tbl[i] = 0u;
+    __syncwarp();
+    bool valid[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) valid[t] = (lane + 32 * t) < cfg.M;
+    uint32_t r = 0;
+    for (int64_t i = w; i < my_imgs; i += bc.NN, r ^= 1u) {
+        float conf[NS];
+        float4 box[NS];
+        int cls[NS];
+        mbar_wait(in_full + w, r);
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            conf[t] = -INFINITY; cls[t] = 0; box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[t]) {
+                const int cell = lane + 32 * t;
+                box[t] = reinterpret_cast<const float4 *>(in)[cell];
+                conf[t] = reinterpret_cast<const float *>(in + MP * 16)[cell];
+                cls[t] = reinterpret_cast<const int *>(in + MP * 20)[cell];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_empty + w);
+        const int64_t img = blockIdx.x + i * gridDim.x;
+        const int K = nms_warp<NS, false>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
+                                          out_idx ? out_idx + img * cfg.M : nullptr);
+        if (lane == 0) out_count[img] = K;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // NMS over already decoded rows (n, M, 6): utils.py:79-114 as a batched call.
 // ------------------------------------------------------------------------------------------
 template <int NS>
@@ -732,6 +1061,13 @@ static int pick_ns(int M)
     return 0;
 }
 
+// whether the division-free filter of suppresses() may be used for this threshold
+static void set_thr(NmsCfg &cfg)
+{
+    const float t = cfg.iou_thr;
+    cfg.thr_fast = (env_int("YH_EXACT_DIV", 0) == 0 && std::isfinite(t) && t > 1e-30f && t < 1e30f) ? 1 : 0;
+}
+
 static int fill_cfg(NmsCfg &cfg, int S, int B, int C, float iou_thr, float conf_thr)
 {
     YH_REQUIRE(S >= 1 && B >= 1 && C >= 1, "decode/nms: S, B, C must be >= 1 (got %d, %d, %d)", S, B, C);
@@ -747,6 +1083,7 @@ static int fill_cfg(NmsCfg &cfg, int S, int B, int C, float iou_thr, float conf_
     cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
     cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr;
     cfg.ws_bytes = 0; cfg.tbl_rows = C; cfg.stage_bytes = 0;
+    set_thr(cfg);
     return YH_OK;
 }
 
@@ -786,6 +1123,48 @@ static int launch_direct(const float *pred, int64_t n, NmsCfg cfg, float *out_bo
     const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * per_sm));
     kern<<<grid, wpb * 32, smem, st>>>(pred, n, cfg, out_boxes, out_count, out_idx);
     YH_LAUNCH_CHECK(bulk_ok ? "decode_nms_warp_tma_kernel" : "decode_nms_direct_kernel");
+    return YH_OK;
+}
+
+// Big images: chunked TMA ring + decode warps + NMS warps (decode_nms_big_kernel).  Returns
+// YH_OK with *launched = false when the shape does not qualify (the caller falls back to the direct kernel).
+template <int NS, int CT, int BT>
+static int launch_big(const float *pred, int64_t n, NmsCfg cfg, float *out_boxes, int *out_count, int *out_idx,
+                      cudaStream_t st, bool *launched)
+{
+    *launched = false;
+    const int64_t img_bytes = 4ll * cfg.M * cfg.D;
+    if (env_int("YH_BIG", 1) == 0 || reinterpret_cast<uintptr_t>(pred) % 16 != 0 || img_bytes % 16 != 0) return YH_OK;
+    BigCfg bc;
+    bc.slots = (cfg.M + 31) / 32;
+    bc.chunk_bytes = 32u * cfg.D * 4u;
+    bc.last_bytes = static_cast<uint32_t>(img_bytes - static_cast<int64_t>(bc.slots - 1) * bc.chunk_bytes);
+    bc.in_bytes = 32 * NS * 24;
+    bc.n = n;
+    cfg.ws_bytes = WarpWs<NS, false>::bytes(cfg.tbl_rows);
+    bc.pairs = (NS > 2 && env_int("YH_BIG_PAIRS", 1) != 0) ? 1 : 0;
+    bc.pair_bytes = bc.pairs ? ((WarpWs<NS, false>::pair_bytes() + 15) & ~15) : 0;
+    const size_t per_nms = static_cast<size_t>(cfg.ws_bytes) + bc.in_bytes + bc.pair_bytes;
+    // at most 16 warps at 128 registers: 1 producer + ND decode + NN NMS.  The ring holds K stages per
+    // decode warp (ST = K * ND, see the kernel comment); ND <= chunks per image.
+    bc.ND = std::max(1, std::min(std::min(8, bc.slots), env_int("YH_BIG_ND", 3)));
+    bc.NN = std::max(1, std::min(15 - bc.ND, env_int("YH_BIG_NN", bc.pairs ? 8 : 10)));
+    int K = std::max(1, std::min(4, env_int("YH_BIG_K", 2)));
+    auto need = [&](int nn, int stg) {
+        return static_cast<size_t>(stg) * bc.chunk_bytes + (2 * static_cast<size_t>(stg) + 2 * nn) * 8 + 16 + nn * per_nms + 128;
+    };
+    while (K > 1 && need(bc.NN, K * bc.ND) > 227 * 1024) --K;
+    while (bc.NN > 2 && need(bc.NN, K * bc.ND) > 227 * 1024) --bc.NN;
+    while (bc.ND > 1 && need(bc.NN, K * bc.ND) > 227 * 1024) --bc.ND;
+    bc.ST = K * bc.ND;
+    if (need(bc.NN, bc.ST) > 227 * 1024 || bc.chunk_bytes % 16 != 0 || bc.last_bytes % 16 != 0) return YH_OK;
+    const size_t smem = need(bc.NN, bc.ST);
+    auto kern = decode_nms_big_kernel<NS, CT, BT>;
+    YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int grid = static_cast<int>(std::min<int64_t>(n, sm_count()));
+    kern<<<grid, 32 * (1 + bc.ND + bc.NN), smem, st>>>(pred, cfg, bc, out_boxes, out_count, out_idx);
+    YH_LAUNCH_CHECK("decode_nms_big_kernel");
+    *launched = true;
     return YH_OK;
 }
 
@@ -834,6 +1213,13 @@ static int launch_fused(const float *pred, int64_t n, NmsCfg cfg, float *out_box
             }
         }
     }
+    // ---- images too large for the tile ring: chunked ring + warp specialisation ----
+    if (done == 0 && img_bytes > 12 * 1024) {
+        bool launched = false;
+        const int rc = launch_big<NS, CT, BT>(pred, n, cfg, out_boxes, out_count, out_idx, st, &launched);
+        if (rc != YH_OK) return rc;
+        if (launched) return YH_OK;
+    }
     // ---- tail / fallback ----
     if (done < n) {
         return launch_direct<NS, CT, BT>(pred + done * cfg.M * cfg.D, n - done, cfg, out_boxes + done * cfg.M * 6,
@@ -855,6 +1241,7 @@ int decode_nms_device(const float *pred, int64_t n, int S, int B, int C, float i
                "decode_nms: pred and out_boxes must be 8-byte aligned");
     const int ns = pick_ns(cfg.M);
     if (ns == 2 && C == 20 && B == 2) return launch_fused<2, 20, 2>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
+    if (ns == 7 && C == 80 && B == 3 && env_int("YH_SPECIAL", 1) != 0) return launch_fused<7, 80, 3>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
     switch (ns) {
         case 1: return launch_fused<1, 0, 0>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
         case 2: return launch_fused<2, 0, 0>(pred, n, cfg, out_boxes, out_count, out_keep_idx, st);
@@ -913,6 +1300,7 @@ extern "C" int yh_nms(const float *boxes, int64_t n, int M, float iou_thr, float
     NmsCfg cfg;
     cfg.S = 0; cfg.B = 0; cfg.C = 0; cfg.M = M; cfg.D = 6; cfg.inv_s = 0.f;
     cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.stage_bytes = 0;
+    set_thr(cfg);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (pick_ns(M)) {
         case 1: return launch_nms_rows<1>(boxes, n, cfg, out_boxes, out_count, out_keep_idx, st);
@@ -931,6 +1319,7 @@ extern "C" int yh_decode(const float *pred, int64_t n, int S, int B, int C, floa
     cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
     cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
     cfg.iou_thr = cfg.conf_thr = 0.f; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.stage_bytes = 0;
+    cfg.thr_fast = 0;
     if (n == 0) return YH_OK;
     YH_REQUIRE(pred && out_boxes, "decode: null pointer");
     YH_REQUIRE(reinterpret_cast<uintptr_t>(out_boxes) % 8 == 0, "decode: out_boxes must be 8-byte aligned");

@@ -1,5 +1,5 @@
 """Short driver for ncu: a few launches of the fused decode+NMS kernel on the cfg2 workload
-(1M dense images unless YH_PROF_IMAGES is set).  `python profiles/prof_decode_nms.py [dense|sparse|stress]`."""
+(1M dense images unless YH_PROF_IMAGES is set).  `python profiles/prof_decode_nms.py [dense|sparse|stress|stress5]` (stress = uniform classes, stress5 = cfg5 data)."""
 import ctypes
 import os
 import sys
@@ -13,7 +13,7 @@ from yolohot import _lib  # noqa: E402
 mode = sys.argv[1] if len(sys.argv) > 1 else "dense"
 n = int(os.environ.get("YH_PROF_IMAGES", 1_000_000))
 S, B, C, thr = 7, 2, 20, 0.4
-if mode == "stress":
+if mode in ("stress", "stress5"):
     S, B, C, thr = 14, 3, 80, 0.05
     n = int(os.environ.get("YH_PROF_IMAGES", 65_536))
 D = C + 5 * B
@@ -21,6 +21,14 @@ dev = torch.device("cuda:0")
 g = torch.Generator(device=dev)
 g.manual_seed(2025)
 p = torch.rand((n, S, S, D), generator=g, device=dev)
+if mode == "stress5":        # cfg5 as specified: ~80 % of the argmaxes in 4 dominant classes, w,h in [0.1, 0.6)
+    dom = torch.randint(0, 4, (n, S, S), generator=g, device=dev)
+    boost = torch.rand((n, S, S), generator=g, device=dev) < 0.8
+    for k in range(4):
+        p[..., k] += 1.5 * (boost & (dom == k)).float()
+    for b in range(B):
+        p[..., C + 5 * b + 3:C + 5 * b + 5] = 0.1 + 0.5 * p[..., C + 5 * b + 3:C + 5 * b + 5]
+    del dom, boost
 if mode == "sparse":
     for b in range(B):
         p[..., C + 5 * b] = p[..., C + 5 * b] ** 32
