@@ -38,6 +38,14 @@ struct NmsCfg {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+#ifndef YH_RANK_INT
+#define YH_RANK_INT 1
+#endif
+// Bits of (a > b) ? 1.0f : 0.0f, i.e. 127 << 23 or 0: one FSET.BF.  The rank loop adds these bit
+// patterns with three-input INTEGER adds (two comparisons per IADD3); the sum is count * 127 * 2^23
+// mod 2^32, and count (< 512) is recovered as ((sum >> 23) * 127^-1) mod 512 with 127^-1 = 383 (mod 512).
+__device__ __forceinline__ int gt_bits(float a, float b) { return __float_as_int((a > b) ? 1.0f : 0.0f); }
+
 // per-warp workspace carve-up (MP = 32 * NS slots).  Only what other lanes must see lives in
 // shared memory: the compact confidences for the rank loop, and per RANK POSITION the box
 // corners / area / class key for the IoU tests and the output slot.  Confidence, box and class
@@ -150,10 +158,29 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
     if (lane < 4) ws.ckey[n + lane] = -INFINITY;   // pad to a multiple of 4 for the float4 loop
     __syncwarp();
 
-    // ---- B: stable descending rank (utils.py:98): r = #{j : s_j > s}; counted in float
-    //      (exact below 2^24) so that each comparison is one FSET + one FADD ----
+    // ---- B: stable descending rank (utils.py:98): r = #{j : s_j > s}.  Each comparison is one
+    //      FSET.BF; two results are folded into the counter by one three-input integer add (see
+    //      gt_bits), i.e. 1.5 instructions per comparison; n <= 256 < 512 ----
     int r[NS];
     {
+#if YH_RANK_INT
+        int acc[NS];
+#pragma unroll
+        for (int t = 0; t < NS; ++t) acc[t] = 0;
+        const float4 *k4p = reinterpret_cast<const float4 *>(ws.ckey);
+        const int n4 = (n + 3) >> 2;
+        for (int g = 0; g < n4; ++g) {
+            const float4 k = k4p[g];
+#pragma unroll
+            for (int t = 0; t < NS; ++t) {
+                const float c = conf[t];
+                acc[t] = acc[t] + gt_bits(k.x, c) + gt_bits(k.y, c);
+                acc[t] = acc[t] + gt_bits(k.z, c) + gt_bits(k.w, c);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NS; ++t) r[t] = ((static_cast<unsigned>(acc[t]) >> 23) * 383u) & 511u;
+#else
         float rf[NS];
 #pragma unroll
         for (int t = 0; t < NS; ++t) rf[t] = 0.0f;
@@ -172,6 +199,7 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
         }
 #pragma unroll
         for (int t = 0; t < NS; ++t) r[t] = static_cast<int>(rf[t]);
+#endif
     }
     // a duplicate rank <=> equal confidences exist: only then pay for the tie-break pass
     {

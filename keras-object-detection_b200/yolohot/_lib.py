@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyolohot.so")
+LIB_PATH = os.environ.get("YH_LIB_PATH") or os.path.join(_HERE, "libyolohot.so")   # YH_LIB_PATH: A/B builds
 
 YH_OK, YH_ERR_ARG, YH_ERR_CUDA, YH_ERR_UNSUPPORTED = 0, -1, -2, -4
 YH_DTYPE_F16, YH_DTYPE_BF16 = 1, 2

@@ -31,3 +31,20 @@ tot_i = sum(r[1] for r in recs)
 print(f"total samples {tot_s:.0f}, warp instructions {tot_i:.4g} = {tot_i / units:.1f} per unit")
 for smp, ins, f, ln, src, st in sorted(recs, reverse=True)[:top]:
     print(f"{100 * smp / tot_s:5.1f}% smp {ins / units:8.1f} inst  {f}:{ln:>4s}  {src}   [{', '.join(f'{k} {v:.0f}' for v, k in st)}]")
+
+# optional phase buckets: YH_BUCKETS="name:lo-hi,name:lo-hi" over lines of the main .cu file
+import os
+spec = os.environ.get("YH_BUCKETS")
+if spec:
+    main = os.environ.get("YH_BUCKET_FILE", "yh_decode_nms.cu")
+    print("phase buckets (share of samples, warp instructions per unit):")
+    rest_s, rest_i = tot_s, tot_i
+    for item in spec.split(","):
+        name, rng = item.split(":")
+        lo, hi = (int(x) for x in rng.split("-"))
+        ss = sum(r[0] for r in recs if r[2] == main and lo <= int(r[3]) <= hi)
+        ii = sum(r[1] for r in recs if r[2] == main and lo <= int(r[3]) <= hi)
+        rest_s -= ss
+        rest_i -= ii
+        print(f"  {name:28s} {100 * ss / tot_s:5.1f}%  {ii / units:8.1f}")
+    print(f"  {'(other files / lines)':28s} {100 * rest_s / tot_s:5.1f}%  {rest_i / units:8.1f}")
