@@ -22,6 +22,8 @@ struct LossCfg {
     float lc, ln;           // lambda_coord, lambda_noobj
     int64_t n_cells;
     int tile_cells;         // cells per shared-memory tile
+    int stages;             // depth of the TMA ring (<= kLossMaxStages)
+    int defer_cap;          // capacity of the deferred heavy-cell list
 };
 
 constexpr int kLossThreads = 128;
@@ -36,21 +38,29 @@ __device__ __forceinline__ double warp_sum(double v)
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
 // Persistent CTAs; each walks its tiles (tile_cells consecutive cells of y_true and y_pred) through a
-// kStages-deep shared-memory ring filled by cp.async.bulk (TMA, one elected thread, mbarrier
-// complete_tx), so the loads of tile i+1.. overlap the arithmetic of tile i; the gradient tile goes
-// back with a bulk shared->global store.  Tiles that are not 16-byte aligned/sized (tail, odd bases)
-// are moved with plain coalesced loads/stores by the whole CTA instead.
-//   pass A  thread per cell: cells without object and with an all-zero true box ("light", ~95 % of a
-//           VOC batch) only owe the no-object term on box 0 (every IoU is exactly +0 there, so the
-//           first-max responsible box is box 0, loss.py:136,197); the others are compacted (ballot)
-//   pass B  one thread per compacted "heavy" cell: IoUs, responsible box, the four box/confidence
-//           terms and their gradients
-//   pass C  class term and gradient, flat over (cell, class) so shared-memory rows are read
-//           conflict-free by consecutive lanes
+// kLossStages-deep shared-memory ring filled by cp.async.bulk (TMA, one elected thread, mbarrier
+// complete_tx), so the loads of tile i+1.. overlap the arithmetic of tile i.  Tiles that are not
+// 16-byte aligned/sized (tail, odd bases) are loaded with plain coalesced loads by the whole CTA.
+//
+// The gradient is almost all zeros (about 95 % of the cells of a VOC batch hold no object, and of a
+// no-object cell only the confidence of box 0 gets a gradient), so it is not assembled element by
+// element: the CTA zero-fills its gradient tile in global memory with 128-bit stores, and the few
+// non-zero entries are written on top afterwards (same CTA, ordered by __syncthreads; both land in
+// L2 before the line is evicted, so DRAM sees full lines once).
+//   pass A  (per tile) thread per cell: cells without object and with an all-zero true box ("light")
+//           only owe the no-object term on box 0 (every IoU is exactly +0 there, so the first-max
+//           responsible box is box 0, loss.py:136,197).  The others ("heavy", ~5 %) are NOT worked on
+//           here - their long dependent chains (divisions, square roots) would stall the whole
+//           tile pipeline for a handful of busy threads: their 2*D values are copied to a deferred
+//           list in shared memory
+//   pass B  (when the list is full, and once at the end) one thread per deferred cell: IoUs,
+//           responsible box, the four box/confidence terms and their gradients
+//   pass C  class term and gradient of the deferred cells with an object: one warp per cell, lanes
+//           over classes (every other cell contributes obj * (...) = 0 exactly, loss.py:206)
 // Sums: per-thread float64 -> warp -> block partials; the last block to finish (ticket counter) adds
 // the partials of all blocks in index order and writes the six outputs: one launch, and the result
 // does not depend on which block came last.
-constexpr int kLossStages = 3;
+constexpr int kLossMaxStages = 8;
 
 template <bool kGrad>
 __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
@@ -63,8 +73,11 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
     const int tile_fl = cfg.tile_cells * D;
     const uint32_t tile_bytes = static_cast<uint32_t>(tile_fl) * 4u;
     float *ring = reinterpret_cast<float *>(smem);                     // [stage][0: y_true tile | 1: y_pred tile]
+    const int kLossStages = cfg.stages;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(kLossStages) * 2 * tile_bytes);
-    int *heavy = reinterpret_cast<int *>(full + kLossStages);           // [tile_cells] compacted heavy cells
+    int *heavy = reinterpret_cast<int *>(full + kLossStages);           // [tile_cells] heavy cells of the current tile
+    int64_t *hcell = reinterpret_cast<int64_t *>(heavy + ((cfg.tile_cells + 1) & ~1));   // [defer_cap] global cell index
+    float *hdat = reinterpret_cast<float *>(hcell + cfg.defer_cap);     // [defer_cap][2 D]: y_true row | y_pred row
     __shared__ double red[kLossThreads / 32][5];
     __shared__ double fin[5][26];
     __shared__ int wcount[kLossThreads / 32];
@@ -73,8 +86,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int64_t n_tiles = (cfg.n_cells + cfg.tile_cells - 1) / cfg.tile_cells;
     const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const bool base_ok = ((reinterpret_cast<uintptr_t>(yt) | reinterpret_cast<uintptr_t>(yp) |
-                           (kGrad ? reinterpret_cast<uintptr_t>(grad) : 0)) % 16 == 0) && (tile_bytes % 16 == 0);
+    const bool base_ok = ((reinterpret_cast<uintptr_t>(yt) | reinterpret_cast<uintptr_t>(yp)) % 16 == 0) && (tile_bytes % 16 == 0);
+    const bool gvec_ok = kGrad && (reinterpret_cast<uintptr_t>(grad) % 16 == 0) && (tile_bytes % 16 == 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < kLossStages; ++s) mbar_init(full + s, 1);
         mbar_fence_init();
@@ -100,74 +113,14 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
             if (is_bulk(it)) issue(it);
 
     double sxy = 0, swh = 0, sob = 0, snb = 0, scl = 0;
-    for (int64_t it = 0; it < my_tiles; ++it) {
-        const int s = static_cast<int>(it % kLossStages);
-        const uint32_t ph = static_cast<uint32_t>((it / kLossStages) & 1);
-        const int64_t cell0 = (blockIdx.x + it * gridDim.x) * cfg.tile_cells;
-        const int cells = tile_cells_of(it);
-        const int nfl = cells * D;
-        float *st = ring + static_cast<size_t>(s) * 2 * tile_fl;
-        float *sp = st + tile_fl;
-        const bool bulk = is_bulk(it);
-        // refill the stage that tile it-1 used (its gradient store must have finished reading it)
-        if (threadIdx.x == 0) {
-            const int64_t nx = it + kLossStages - 1;
-            if (nx < my_tiles && is_bulk(nx)) {
-                bulk_store_wait_read_all();
-                issue(nx);
-            }
-        }
-        if (bulk) {
-            mbar_wait(full + s, ph);
-        } else {
-            if (threadIdx.x == 0) bulk_store_wait_read_all();
-            __syncthreads();
-            const float *gt = yt + cell0 * D, *gp = yp + cell0 * D;
-            for (int i = threadIdx.x; i < nfl; i += blockDim.x) {
-                st[i] = gt[i];
-                sp[i] = gp[i];
-            }
-            __syncthreads();
-        }
-
-        // ---- pass A: light cells + compaction of the heavy ones ----
-        int n_heavy = 0;
-        for (int c0 = 0; c0 < cells; c0 += blockDim.x) {
-            const int cell = c0 + threadIdx.x;
-            bool hv = false;
-            if (cell < cells) {
-                const float *t = st + cell * D;
-                float *p = sp + cell * D;
-                const float obj = t[C];
-                hv = (obj != 0.0f) || (t[C + 1] != 0.0f) || (t[C + 2] != 0.0f) || (t[C + 3] != 0.0f) || (t[C + 4] != 0.0f);
-                if (!hv) {
-                    const float c = p[C];                                     // responsible = box 0
-                    const float noobj = __fsub_rn(1.0f, obj);                 // loss.py:163
-                    const float z = __fsub_rn(0.0f, c);
-                    snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));   // loss.py:197
-                    if (kGrad) {
-                        for (int j = C + 1; j < D; ++j) p[j] = 0.f;
-                        p[C] = cfg.ln * 2.0f * noobj * c;
-                    }
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, hv);
-            if (lane == 0) wcount[warp] = __popc(bal);
-            __syncthreads();
-            int base = n_heavy;
-            for (int w = 0; w < warp; ++w) base += wcount[w];
-            if (hv) heavy[base + __popc(bal & ((1u << lane) - 1u))] = cell;
-            for (int w = 0; w < nwarp; ++w) n_heavy += wcount[w];
-            __syncthreads();
-        }
-
-        // ---- pass B: heavy cells, one thread each; cell h goes to warp h % nwarp so that the few
-        //      heavy cells of a tile (long dependent chains: divisions, square roots) run in parallel
-        //      on different warps instead of side by side in one ----
-        for (int h = lane * nwarp + warp; h < n_heavy; h += 32 * nwarp) {
-            const int cell = heavy[h];
-            const float *t = st + cell * D;
-            float *p = sp + cell * D;
+    int n_def = 0;                                  // deferred heavy cells (CTA-uniform)
+    // pass B + C over the deferred list; called by all threads
+    auto flush = [&]() {
+        __syncthreads();                                                      // list complete
+        for (int h = threadIdx.x; h < n_def; h += blockDim.x) {
+            const float *t = hdat + h * 2 * D;
+            const float *p = t + D;
+            float *gc = kGrad ? grad + hcell[h] * D : nullptr;
             const float obj = t[C];                                           // loss.py:162
             const float tx = t[C + 1], ty = t[C + 2], tw = t[C + 3], th = t[C + 4];
             int k = 0;                                                        // loss.py:126-137
@@ -177,7 +130,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
                 const float v = iou_ref(tx, ty, tw, th, q[1], q[2], q[3], q[4]);
                 if (v > u) { u = v; k = b; }
             }
-            float *q = p + C + 5 * k;
+            const float *q = p + C + 5 * k;
             const float c = q[0], px = q[1], py = q[2], pw = q[3], ph_ = q[4];
             const float noobj = __fsub_rn(1.0f, obj);
             const float z = __fsub_rn(0.0f, c);
@@ -229,43 +182,108 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
                     g_w = -2.0f * cfg.lc * obj * dw * (sw * sw) / (2.0f * rw) + e2 * du_dpw;
                     g_h = -2.0f * cfg.lc * obj * dh * (sh * sh) / (2.0f * rh) + e2 * du_dph;
                 }
-                for (int j = C; j < D; ++j) p[j] = 0.f;
-                q[0] = g_c; q[1] = g_x; q[2] = g_y; q[3] = g_w; q[4] = g_h;
+                float *gq = gc + C + 5 * k;                                   // every other box of the cell stays 0
+                gq[0] = g_c; gq[1] = g_x; gq[2] = g_y; gq[3] = g_w; gq[4] = g_h;
             }
+        }
+        for (int h = warp; h < n_def; h += nwarp) {
+            const float *t = hdat + h * 2 * D;
+            const float obj = t[C];
+            if (obj != 0.0f) {                                                // loss.py:206
+                float *gc = kGrad ? grad + hcell[h] * D : nullptr;
+                for (int j = lane; j < C; j += 32) {
+                    const float d = __fsub_rn(t[j], t[D + j]);
+                    scl += static_cast<double>(__fmul_rn(obj, __fmul_rn(d, d)));
+                    if (kGrad) gc[j] = -2.0f * obj * d;
+                }
+            }
+        }
+        __syncthreads();                                                      // list may be refilled
+    };
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int s = static_cast<int>(it % kLossStages);
+        const uint32_t ph = static_cast<uint32_t>((it / kLossStages) & 1);
+        const int64_t cell0 = (blockIdx.x + it * gridDim.x) * cfg.tile_cells;
+        const int cells = tile_cells_of(it);
+        const int nfl = cells * D;
+        const float *st = ring + static_cast<size_t>(s) * 2 * tile_fl;
+        const float *sp = st + tile_fl;
+        float *gg = kGrad ? grad + cell0 * D : nullptr;
+        const bool bulk = is_bulk(it);
+        // refill the stage that tile it-1 used (every thread left it at the barrier that ends an iteration)
+        if (threadIdx.x == 0) {
+            const int64_t nx = it + kLossStages - 1;
+            if (nx < my_tiles && is_bulk(nx)) issue(nx);
+        }
+        // ---- gradient tile := 0 (overwritten below where it is not) ----
+        if (kGrad) {
+            if (gvec_ok && cells == cfg.tile_cells) {
+                float4 *g4 = reinterpret_cast<float4 *>(gg);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = threadIdx.x; i < (nfl >> 2); i += blockDim.x) g4[i] = z;
+            } else {
+                for (int i = threadIdx.x; i < nfl; i += blockDim.x) gg[i] = 0.f;
+            }
+        }
+        if (bulk) {
+            mbar_wait(full + s, ph);
+        } else {
+            const float *gt = yt + cell0 * D, *gp = yp + cell0 * D;
+            float *wt = ring + static_cast<size_t>(s) * 2 * tile_fl;
+            for (int i = threadIdx.x; i < nfl; i += blockDim.x) {
+                wt[i] = gt[i];
+                wt[tile_fl + i] = gp[i];
+            }
+            __syncthreads();
         }
 
-        // ---- pass C: class term, flat over (cell, class); touches only channels < C ----
-        {
-            const int total = cells * C;
-            int cell = threadIdx.x / C, j = threadIdx.x % C;
-            const int dc = blockDim.x / C, dj = blockDim.x % C;
-            for (int e_ = threadIdx.x; e_ < total; e_ += blockDim.x) {
-                const float obj = st[cell * D + C];
-                float *pp = sp + cell * D + j;
-                if (obj != 0.0f) {                                            // loss.py:206
-                    const float d = __fsub_rn(st[cell * D + j], *pp);
-                    scl += static_cast<double>(__fmul_rn(obj, __fmul_rn(d, d)));
-                    if (kGrad) *pp = -2.0f * obj * d;
-                } else if (kGrad) {
-                    *pp = 0.0f;
+        // ---- pass A: light cells + compaction of the heavy ones ----
+        int n_heavy = 0;
+        for (int c0 = 0; c0 < cells; c0 += blockDim.x) {
+            const int cell = c0 + threadIdx.x;
+            bool hv = false;
+            float g_light = 0.f;
+            if (cell < cells) {
+                const float *t = st + cell * D;
+                const float obj = t[C];
+                hv = (obj != 0.0f) || (t[C + 1] != 0.0f) || (t[C + 2] != 0.0f) || (t[C + 3] != 0.0f) || (t[C + 4] != 0.0f);
+                if (!hv) {
+                    const float c = sp[cell * D + C];                         // responsible = box 0
+                    const float noobj = __fsub_rn(1.0f, obj);                 // loss.py:163
+                    const float z = __fsub_rn(0.0f, c);
+                    snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));   // loss.py:197
+                    g_light = cfg.ln * 2.0f * noobj * c;
                 }
-                cell += dc; j += dj;
-                if (j >= C) { j -= C; ++cell; }
             }
+            const unsigned bal = __ballot_sync(0xffffffffu, hv);
+            if (lane == 0) wcount[warp] = __popc(bal);
+            __syncthreads();                                                  // also: zero fill before the stores below
+            int base = n_heavy;
+            for (int w = 0; w < warp; ++w) base += wcount[w];
+            if (hv) heavy[base + __popc(bal & ((1u << lane) - 1u))] = cell;
+            if (kGrad && cell < cells && !hv) gg[cell * D + C] = g_light;
+            for (int w = 0; w < nwarp; ++w) n_heavy += wcount[w];
+            __syncthreads();
         }
-        if (kGrad && bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my tile writes -> async proxy
-        __syncthreads();
-        if (kGrad) {
-            float *gg = grad + cell0 * D;
-            if (bulk) {
-                if (threadIdx.x == 0) bulk_s2g(gg, sp, tile_bytes);
-            } else {
-                for (int i = threadIdx.x; i < nfl; i += blockDim.x) gg[i] = sp[i];
-                __syncthreads();
+        // ---- defer the heavy cells of this tile (flush first if they would not fit) ----
+        for (int h0 = 0; h0 < n_heavy;) {
+            if (n_def == cfg.defer_cap) {
+                flush();
+                n_def = 0;
             }
+            const int take = min(n_heavy - h0, cfg.defer_cap - n_def);
+            for (int e = threadIdx.x; e < take * 2 * D; e += blockDim.x) {
+                const int h = e / (2 * D), j = e - h * 2 * D;
+                const int cell = heavy[h0 + h];
+                hdat[(n_def + h) * 2 * D + j] = (j < D) ? st[cell * D + j] : sp[cell * D + j - D];
+            }
+            for (int h = threadIdx.x; h < take; h += blockDim.x) hcell[n_def + h] = cell0 + heavy[h0 + h];
+            n_def += take;
+            h0 += take;
         }
+        __syncthreads();              // everybody is done with this stage and with heavy[]
     }
-    if (threadIdx.x == 0) bulk_store_wait_all();
+    if (n_def > 0) flush();
 
     // stage 1 of the deterministic reduction: lanes -> warp -> block, fixed order
     sxy = warp_sum(sxy); swh = warp_sum(swh); sob = warp_sum(sob); snb = warp_sum(snb); scl = warp_sum(scl);
@@ -288,11 +306,23 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // thread i: term i % 5, blocks (i / 5), (i / 5) + 25, ...; then 25 sub-sums per term in index order
+    // thread i: term i % 5, blocks (i / 5), (i / 5) + 25, ...; then 25 sub-sums per term in index order.
+    // The loads of a thread are issued together (one L2 round trip, not one per block) and added in
+    // block order afterwards.
     const int term = threadIdx.x % 5, slot = threadIdx.x / 5;
     if (slot < 25) {
         double s = 0;
-        for (int b = slot; b < static_cast<int>(gridDim.x); b += 25) s += __ldcg(partials + static_cast<size_t>(b) * 5 + term);
+        const int nb = static_cast<int>(gridDim.x);
+        for (int b0 = slot; b0 < nb; b0 += 25 * 16) {
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int b = b0 + 25 * j;
+                v[j] = (b < nb) ? __ldcg(partials + static_cast<size_t>(b) * 5 + term) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s += v[j];
+        }
         fin[term][slot] = s;
     }
     __syncthreads();
@@ -341,10 +371,20 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LossCfg cfg;
     cfg.B = B; cfg.C = C; cfg.D = C + 5 * B; cfg.lc = lambda_coord; cfg.ln = lambda_noobj; cfg.n_cells = n_cells;
-    int tile = 128;                      // cells per tile; ring = kLossStages x (y_true + y_pred tile)
-    auto smem_of = [&](int tl) { return static_cast<size_t>(kLossStages) * 2 * tl * cfg.D * 4 + kLossStages * 8 + static_cast<size_t>(tl) * 4 + 64; };
-    static const int smem_cap_kb = [] { const char *v = getenv("YH_LOSS_SMEM_KB"); return (v && *v) ? atoi(v) : 72; }();
-    while (tile > 16 && smem_of(tile) > static_cast<size_t>(smem_cap_kb) * 1024) tile >>= 1;
+    // tile / ring geometry: small tiles keep the static tile split even across the persistent CTAs (the
+    // cfg3 batch is only ~10 tiles per CTA) and a deep ring keeps >= 44 KB per SM in flight
+    static const int env_tile = [] { const char *v = getenv("YH_LOSS_TILE"); return (v && *v) ? atoi(v) : 64; }();
+    static const int env_stages = [] { const char *v = getenv("YH_LOSS_STAGES"); return (v && *v) ? atoi(v) : 2; }();
+    static const int env_ctas = [] { const char *v = getenv("YH_LOSS_CTAS"); return (v && *v) ? atoi(v) : 4; }();
+    int tile = std::max(16, std::min(1024, env_tile));
+    cfg.stages = std::max(2, std::min(kLossMaxStages, env_stages));
+    static const int env_defer = [] { const char *v = getenv("YH_LOSS_DEFER"); return (v && *v) ? atoi(v) : 64; }();
+    cfg.defer_cap = std::max(8, std::min(std::min(128, env_defer), (24 * 1024) / (8 * cfg.D)));
+    auto smem_of = [&](int tl) {
+        return static_cast<size_t>(cfg.stages) * 2 * tl * cfg.D * 4 + cfg.stages * 8 + static_cast<size_t>(tl + 2) * 4 +
+               static_cast<size_t>(cfg.defer_cap) * (8 + 8 * cfg.D) + 64;
+    };
+    while (tile > 16 && smem_of(tile) > static_cast<size_t>(100) * 1024) tile >>= 1;
     const size_t smem = smem_of(tile);
     if (smem > 227 * 1024) {
         set_error("loss: C + 5B = %d too large for the shared-memory tile", cfg.D);
@@ -368,7 +408,7 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
         g.per_sm = per_sm < 1 ? 1 : per_sm;
     }
     const int grid = static_cast<int>(
-        std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * g.per_sm)));
+        std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * std::min(g.per_sm, std::max(1, env_ctas)))));
     LossScratch &sc = g_loss[dev];
     if (sc.cap_blocks < grid) {
         if (sc.partials) {
