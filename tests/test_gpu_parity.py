@@ -366,3 +366,93 @@ def test_sharded_map_single_process_emulation(dev):
             ks.append(k); ts.append(t); gs = gs + g
         m, _ = yu.map_reduce(torch.cat(ks), torch.cat(ts), gs, 20)
         assert float(m) == whole
+
+
+# ------------------------------------------------------------ BASELINE.json configs at full size
+def _dense_cfg5(n, dev, seed=99):
+    """cfg5 data on the device (same recipe as profiles/bench_configs.py)."""
+    S, B, C = 14, 3, 80
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    p = torch.rand((n, S, S, C + 5 * B), generator=g, device=dev)
+    dom = torch.randint(0, 4, (n, S, S), generator=g, device=dev)
+    boost = torch.rand((n, S, S), generator=g, device=dev) < 0.8
+    for k in range(4):
+        p[..., k] += 1.5 * (boost & (dom == k)).float()
+    for b in range(B):
+        p[..., C + 5 * b + 3:C + 5 * b + 5] = 0.1 + 0.5 * p[..., C + 5 * b + 3:C + 5 * b + 5]
+    return p
+
+
+def _full_size_checks(yu, p, C, B, it, ct, audit, what):
+    """Oracle (C port) on audit slices of the batch + size-independent properties on all of it."""
+    n, M = p.shape[0], p.shape[1] * p.shape[2]
+    boxes, cnt, kidx = yu.decode_nms(p, C, B, it, ct, return_index=True)
+    for lo in (0, n // 2 - audit // 2, n - audit):                       # head, middle and tail of the batch
+        want = cport.decode_nms(p[lo:lo + audit].cpu().numpy(), C, B, it, ct, nthreads=cport.num_threads())
+        _check_nms((boxes[lo:lo + audit], cnt[lo:lo + audit], kidx[lo:lo + audit]), want, f"{what} slice@{lo}")
+    m = torch.arange(M, device=p.device)[None, :] < cnt[:, None]
+    conf = boxes[..., 1]
+    assert bool((torch.where(m, conf, torch.full_like(conf, float("inf"))) > ct).all())           # strict filter
+    c2 = torch.where(m, conf, torch.zeros_like(conf))
+    assert bool((c2[:, 1:] <= c2[:, :-1]).all())                                                  # pick order
+    # an image's result depends on that image only: any permutation of the batch permutes the result
+    perm = torch.randperm(n, device=p.device, generator=torch.Generator(device=p.device).manual_seed(1))
+    b2, c2n, k2 = yu.decode_nms(p[perm], C, B, it, ct, return_index=True)
+    assert torch.equal(c2n, cnt[perm])
+    assert torch.equal(torch.where(m[perm], k2, torch.full_like(k2, -1)), torch.where(m, kidx, torch.full_like(kidx, -1))[perm])
+    assert torch.equal(b2[m[perm]], boxes[perm][m[perm]])
+    return int(cnt.sum())
+
+
+def test_cfg2_full_size_one_million_images(dev):
+    """BASELINE configs[1]: 1,000,000 dense VOC-shaped outputs, TMA tile ring."""
+    from yolohot import utils as yu
+    g = torch.Generator(device=dev)
+    g.manual_seed(2025)
+    p = torch.rand((1_000_000, 7, 7, 30), generator=g, device=dev)
+    kept = _full_size_checks(yu, p, 20, 2, 0.5, 0.4, 16384, "cfg2")
+    assert 39.0 < kept / 1e6 < 41.0
+
+
+def test_cfg5_full_size_stress(dev):
+    """BASELINE configs[4]: S=14 B=3 C=80, conf threshold 0.05, 131,072 images (9.76 GB), big-image kernel."""
+    from yolohot import utils as yu
+    p = _dense_cfg5(131_072, dev)
+    kept = _full_size_checks(yu, p, 80, 3, 0.5, 0.05, 2048, "cfg5")
+    assert kept / 131_072 > 100
+
+
+def test_cfg3_full_size_loss_batch_4096(dev):
+    """BASELINE configs[2]: loss forward + backward at batch 4096 against the C port / NumPy oracle."""
+    from yolohot import loss as yl
+    yt = F.synth_labels(4096, seed=7)
+    yp = F.synth_loss_pred(yt.shape, seed=7)
+    terms, grad = yl.yolo_v1_loss_terms(_cuda(yt, dev), _cuda(yp, dev), grad=True)
+    want = cport.loss(yt, yp, 20, 2)
+    np.testing.assert_allclose(terms.cpu().numpy(), want, rtol=1e-5)
+    g_ref = O.yolo_v1_loss_grad(yt[:256], yp[:256])
+    np.testing.assert_allclose(grad[:256].cpu().numpy(), g_ref, rtol=1e-4, atol=1e-4)
+    # the gradient is zero wherever the closed form says so (most of the tensor), everywhere in the batch
+    nz = (grad != 0).float().mean().item()
+    assert 0.01 < nz < 0.15
+    again, _ = yl.yolo_v1_loss_terms(_cuda(yt, dev), _cuda(yp, dev), grad=True)
+    assert torch.equal(again, terms)                                     # run-to-run identical
+
+
+def test_cfg4_full_size_map_5000_images(dev):
+    """BASELINE configs[3]: mAP@0.5 over 5,000 images, streamed in batches, against the C port."""
+    from yolohot import utils as yu
+    yt = F.synth_labels(5000, seed=11)
+    mp = F.synth_map_pred(yt)
+    ev = yu.MeanAveragePrecision(20, 2)
+    for lo in range(0, 5000, 512):
+        ev.update_state(_cuda(yt[lo:lo + 512], dev), _cuda(mp[lo:lo + 512], dev))
+    t_rows = ev.all_true_boxes_variable.cpu().numpy()
+    p_rows = ev.all_pred_boxes_variable.cpu().numpy()
+    pb, pc, _ = cport.decode_nms(mp, 20, 2, nthreads=cport.num_threads())
+    assert p_rows.shape[0] == int(pc.sum())
+    want, want_ap = cport.mean_average_precision(t_rows, p_rows, 20)
+    got, ap = yu.mean_average_precision(_cuda(t_rows, dev), _cuda(p_rows, dev), 20, return_ap=True)
+    assert abs(float(ev.result()) - float(want)) <= 1e-6 and abs(float(got) - float(want)) <= 1e-6
+    np.testing.assert_allclose(ap.cpu().numpy(), want_ap, atol=1e-6)
