@@ -247,6 +247,17 @@ def run_own(args):
                                         h_cnt.data_ptr(), None, local), "yh_decode_nms_host")
 
     e2e_step()
+    # the e2e path's own roofline: a bare pinned H2D copy of the same input (PCIe), device-timed
+    d_tmp = torch.empty_like(pred[:e2e_n])
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_tmp.copy_(h_in, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    c0.record(stream)
+    d_tmp.copy_(h_in, non_blocking=True)
+    c1.record(stream)
+    torch.cuda.synchronize(dev)
+    h2d_gbs = e2e_n * IMG_IN / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del d_tmp
     e2e_steps = max(2, min(args.steps, env_int("YH_BENCH_E2E_STEPS", 5)))
     with ClockSampler(local) as clk2:
         barrier()
@@ -263,7 +274,8 @@ def run_own(args):
     e2e = {"value": world * e2e_n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e_n * IMG_IN,
            "d2h_bytes_per_step": e2e_n * (M * 24 + 4), "images_per_step_per_gpu": e2e_n, "steps": e2e_steps,
            "ms_per_step": 1000.0 * e2e_s, "api": "yh_decode_nms_host (C-ABI, pinned host buffers in/out)",
-           "counts_match_device_path": ok_e2e}
+           "counts_match_device_path": ok_e2e, "bare_pinned_h2d_copy_GBps": h2d_gbs,
+           "frac_of_bare_h2d_copy": (e2e_n * IMG_IN / e2e_s / 1e9) / h2d_gbs}
     del h_in, h_boxes
 
     # ---- CPU baseline (rank 0, N=1 only): oracle C port on a bounded slice of the same inputs
@@ -359,6 +371,26 @@ def other_configs(torch, dev, L, _lib, yu, sp):
     out["cfg3_loss_fwd_bwd_b4096"] = {"ms": ms, "ms_min": mn, "GBps": gbs, "frac_hbm": gbs / peak, "loss": float(terms[5]),
                                       "l2": "8 rotating buffer sets (578 MB > L2), back-to-back launches"}
     del sets
+    # cfg5: stress S=14 B=3 C=80, conf threshold 0.05, ~80 % of the argmaxes in 4 dominant classes
+    S5, B5, C5 = 14, 3, 80
+    n5 = env_int("YH_BENCH_CFG5_IMAGES", 65_536)
+    gen = torch.Generator(device=dev); gen.manual_seed(99)
+    p5 = torch.rand((n5, S5, S5, C5 + 5 * B5), generator=gen, device=dev)
+    dom = torch.randint(0, 4, (n5, S5, S5), generator=gen, device=dev)
+    boost = torch.rand((n5, S5, S5), generator=gen, device=dev) < 0.8
+    for k in range(4):
+        p5[..., k] += 1.5 * (boost & (dom == k)).float()
+    for b in range(B5):
+        p5[..., C5 + 5 * b + 3:C5 + 5 * b + 5] = 0.1 + 0.5 * p5[..., C5 + 5 * b + 3:C5 + 5 * b + 5]
+    del dom, boost
+    boxes5 = torch.empty((n5, S5 * S5, 6), device=dev); cnt5 = torch.empty((n5,), device=dev, dtype=torch.int32)
+    f5 = lambda: _lib.check(L.yh_decode_nms(p5.data_ptr(), n5, S5, B5, C5, IOU_THR, 0.05, boxes5.data_ptr(), cnt5.data_ptr(), None, sp))
+    ms, mn = timed(f5, 10)
+    kept5 = int(cnt5.sum().item())
+    gbs = (n5 * (4 * S5 * S5 * (C5 + 5 * B5) + 4) + 24 * kept5) / (ms * 1e-3) / 1e9
+    out["cfg5_stress"] = {"images": n5, "images_per_s": n5 / (ms * 1e-3), "ms": ms, "GBps": gbs, "frac_hbm": gbs / peak,
+                          "kept_per_image": kept5 / n5, "kernel": "decode_nms_big_kernel<7,80,3>"}
+    del p5, boxes5, cnt5
     # cfg4: mAP over 5k images, single GPU (evaluator update + result)
     yt5 = F.synth_labels(5000, seed=11); mp5 = F.synth_map_pred(yt5)
     a, b_ = torch.from_numpy(yt5).to(dev), torch.from_numpy(mp5).to(dev)

@@ -258,12 +258,17 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
         const bool ac = q < n;
         act_m |= ac ? (1u << t) : 0u;
         qkey[t] = ac ? ws.smeta[q] : 0;
-        if (t < NT) {
-            const unsigned m = __match_any_sync(FULL, ac ? qkey[t] : (0x7f000000 + lane));
-            if (ac && (__ffs(m) - 1) == lane) {
-                ws.tbl[qkey[t] * NS + t] = m;
-                lead |= 1u << t;
-            }
+    }
+    // all MATCH instructions are issued back to back (their latency overlaps), the table is written afterwards
+    unsigned mm[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t)
+        mm[t] = (t < NT) ? __match_any_sync(FULL, ((act_m >> t) & 1u) ? qkey[t] : (0x7f000000 + lane)) : 0u;
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        if (t < NT && ((act_m >> t) & 1u) && (__ffs(mm[t]) - 1) == lane) {
+            ws.tbl[qkey[t] * NS + t] = mm[t];
+            lead |= 1u << t;
         }
     }
     __syncwarp();
