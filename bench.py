@@ -146,6 +146,36 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank (and therefore the first-touch placement of its pinned host buffers) to the CPUs of the
+    NUMA node its GPU hangs off, so that the e2e H2D/D2H copies of 8 ranks do not cross the socket
+    interconnect.  Placement only; returns a description for the JSON line (None if nothing was done)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                       # nvml pads the PCI domain to 8 hex digits
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------ own arm
 def run_own(args):
     import numpy as np
@@ -158,6 +188,7 @@ def run_own(args):
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    numa = bind_to_gpu_numa_node(local) if (world > 1 and env_int("YH_BENCH_NUMA_BIND", 1)) else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -274,7 +305,7 @@ def run_own(args):
     e2e = {"value": world * e2e_n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e_n * IMG_IN,
            "d2h_bytes_per_step": e2e_n * (M * 24 + 4), "images_per_step_per_gpu": e2e_n, "steps": e2e_steps,
            "ms_per_step": 1000.0 * e2e_s, "api": "yh_decode_nms_host (C-ABI, pinned host buffers in/out)",
-           "counts_match_device_path": ok_e2e, "bare_pinned_h2d_copy_GBps": h2d_gbs,
+           "counts_match_device_path": ok_e2e, "numa_binding_rank0": numa, "bare_pinned_h2d_copy_GBps": h2d_gbs,
            "frac_of_bare_h2d_copy": (e2e_n * IMG_IN / e2e_s / 1e9) / h2d_gbs}
     del h_in, h_boxes
 

@@ -1001,6 +1001,266 @@ __global__ void __launch_bounds__(512, 1) decode_nms_big_kernel(const float *__r
 }
 
 // ------------------------------------------------------------------------------------------
+// Cooperative kernel for big images: a TEAM of TW = ceil(M/32) warps works on one image, one
+// THREAD per grid cell / candidate / rank position, phases separated by named barriers
+// (bar.sync id, TW*32); NTEAM teams per CTA run different images so that one team's barrier
+// and load latencies are covered by the others.  Compared with one warp per image the serial
+// chain per image is TW times shorter, the per-image state is ~11 KB per TEAM (not per warp), and
+// the suppression bits of a candidate live in its own registers (no shared-memory bit rows).
+//   warp 0           producer: cp.async.bulk of 32-cell chunks, in image order, into an ST-deep ring;
+//                    after issuing chunk c it publishes c + 1 in `issued`
+//   team T, warp t   consumes chunk t of the images T, T + NTEAM, ... of this CTA.  A consumer first
+//                    waits until `issued` > c (then the stage's barrier is in the phase of chunk c and
+//                    the parity wait is unambiguous for any ring depth), then on full[c % ST]
+// Phases of a team (thread q = 32 * warp + lane is cell q, later rank position q):
+//   A  decode own cell, release the stage;  A' ballot compaction across the team's warps
+//   B  rank by counting over the compact confidences (+ tie pass if a duplicate rank shows up)
+//   C  scatter corners / area / class to rank order; match.any per warp -> class table [class][warp]
+//   D  own same-class predecessors (words 0..warp of the class row) -> suppression words in registers
+//   E  greedy keep flags: fixed point on the team's ballot words (exact, see nms_warp)
+//   F  output slots from the final keep words; every cell thread writes its own row
+// ------------------------------------------------------------------------------------------
+constexpr int kTeamWarpsMax = 8;
+
+struct CoopCfg {
+    int ST, NTEAM, TW;      // ring stages, teams per CTA, warps per team (= chunks per image)
+    uint32_t chunk_bytes, last_bytes;
+    int team_bytes;         // shared memory per team
+    int64_t n;
+};
+
+__device__ __forceinline__ void team_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool team_any(int id, int nthreads, bool p)
+{
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred q, o;\n\t"
+        "setp.ne.s32 q, %3, 0;\n\t"
+        "bar.red.or.pred o, %1, %2, q;\n\t"
+        "selp.s32 %0, 1, 0, o;\n\t}"
+        : "=r"(r)
+        : "r"(id), "r"(nthreads), "r"(static_cast<int>(p))
+        : "memory");
+    return r != 0;
+}
+
+template <int CT, int BT>
+__global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const float *__restrict__ pred, NmsCfg cfg, CoopCfg cc,
+                                                                  float *__restrict__ out_boxes, int *__restrict__ out_count,
+                                                                  int *__restrict__ out_idx)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *ring = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(cc.ST) * cc.chunk_bytes);
+    uint64_t *empty = full + cc.ST;
+    volatile int64_t *issued = reinterpret_cast<volatile int64_t *>(empty + cc.ST);
+    unsigned char *teams = reinterpret_cast<unsigned char *>(const_cast<int64_t *>(issued) + 2);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cc.ST; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        *issued = 0;
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t my_imgs = (cc.n > blockIdx.x) ? (cc.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_chunks = my_imgs * cc.TW;
+    const int64_t img_bytes = 4ll * cfg.M * cfg.D;
+
+    if (warp == 0) {                                               // ---- producer
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(pred);
+            int s = 0, t = 0;
+            uint32_t ph = 0;
+            int64_t i = 0;
+            for (int64_t c = 0; c < n_chunks; ++c) {
+                mbar_wait_relaxed(empty + s, ph ^ 1u, 64);
+                const uint32_t bytes = (t == cc.TW - 1) ? cc.last_bytes : cc.chunk_bytes;
+                mbar_arrive_expect_tx(full + s, bytes);
+                bulk_g2s(ring + static_cast<size_t>(s) * cc.chunk_bytes,
+                         src + (blockIdx.x + i * gridDim.x) * img_bytes + static_cast<size_t>(t) * cc.chunk_bytes, bytes,
+                         full + s, pol);
+                __threadfence_block();
+                *issued = c + 1;
+                if (++s == cc.ST) { s = 0; ph ^= 1u; }
+                if (++t == cc.TW) { t = 0; ++i; }
+            }
+        }
+        return;
+    }
+    const int team = (warp - 1) / cc.TW, wt = (warp - 1) % cc.TW;   // team, warp within the team
+    if (team >= cc.NTEAM) return;
+    const int q = 32 * wt + lane;                                   // cell index, later rank position
+    const int nthr = cc.TW * 32, bar_id = 1 + team;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // team workspace
+    unsigned char *tp = teams + static_cast<size_t>(team) * cc.team_bytes;
+    const int MPT = cc.TW * 32;
+    float4 *scor = reinterpret_cast<float4 *>(tp);           tp += MPT * 16;
+    float *sarea = reinterpret_cast<float *>(tp);            tp += MPT * 4;
+    int *smeta = reinterpret_cast<int *>(tp);                tp += MPT * 4;
+    float *ckey = reinterpret_cast<float *>(tp);             tp += (MPT + 4) * 4;
+    int *outpos = reinterpret_cast<int *>(tp);               tp += MPT * 4;
+    int *wcnt = reinterpret_cast<int *>(tp);                 tp += kTeamWarpsMax * 4;
+    unsigned *kws = reinterpret_cast<unsigned *>(tp);        tp += kTeamWarpsMax * 4;
+    unsigned *tbl = reinterpret_cast<unsigned *>(tp);        // [C][TW]
+    for (int i = q; i < cfg.C * cc.TW; i += nthr) tbl[i] = 0u;
+    team_sync(bar_id, nthr);
+
+    const bool valid = q < cfg.M;
+    const int row = q / cfg.S, col = q - row * cfg.S;
+    const float rowf = static_cast<float>(row), colf = static_cast<float>(col);
+
+    for (int64_t i = team; i < my_imgs; i += cc.NTEAM) {
+        const int64_t img = blockIdx.x + i * gridDim.x;
+        // ---- A: decode own cell from the ring
+        const int64_t c = i * cc.TW + wt;
+        const int s = static_cast<int>(c % cc.ST);
+        const uint32_t ph = static_cast<uint32_t>((c / cc.ST) & 1);
+        while (*issued <= c) __nanosleep(32);
+        mbar_wait(full + s, ph);
+        int cls = 0;
+        float conf = -INFINITY;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid)
+            decode_cell<CT, BT>(reinterpret_cast<const float *>(ring + static_cast<size_t>(s) * cc.chunk_bytes) + lane * cfg.D, cfg,
+                                colf, rowf, cls, conf, box);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+        // ---- A': compaction (utils.py:95, strict >)
+        const bool pass = valid && (conf > cfg.conf_thr);
+        const unsigned bal = __ballot_sync(FULL, pass);
+        if (lane == 0) wcnt[wt] = __popc(bal);
+        team_sync(bar_id, nthr);
+        int n = 0, ci = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kTeamWarpsMax; ++w2) {
+            if (w2 < cc.TW) {
+                const int k = wcnt[w2];
+                if (w2 < wt) ci += k;
+                n += k;
+            }
+        }
+        ci += __popc(bal & lt_mask);
+        if (n == 0) {                                              // team-uniform
+            if (q == 0) out_count[img] = 0;
+            team_sync(bar_id, nthr);                               // wcnt is rewritten by the next image
+            continue;
+        }
+        if (pass) ckey[ci] = conf;
+        if (q < 4) ckey[n + q] = -INFINITY;                        // pad to a multiple of 4 for the float4 loop
+        team_sync(bar_id, nthr);
+        // ---- B: stable descending rank (utils.py:98)
+        int r;
+        {
+            int acc = 0;
+            const float4 *k4p = reinterpret_cast<const float4 *>(ckey);
+            const int n4 = (n + 3) >> 2;
+#pragma unroll 4
+            for (int g = 0; g < n4; ++g) {
+                const float4 k = k4p[g];
+                acc = acc + gt_bits(k.x, conf) + gt_bits(k.y, conf);
+                acc = acc + gt_bits(k.z, conf) + gt_bits(k.w, conf);
+            }
+            r = ((static_cast<unsigned>(acc) >> 23) * 383u) & 511u;
+        }
+        if (!pass) r = 0;                                          // keeps every index below in range
+        if (pass) smeta[r] = ci;
+        team_sync(bar_id, nthr);
+        const bool dup = team_any(bar_id, nthr, pass && smeta[r] != ci);
+        if (dup) {                                                 // equal confidences exist: lower source index first
+            for (int j = 0; j < n; ++j) r += (pass && j < ci && ckey[j] == conf) ? 1 : 0;
+        }
+        // ---- C: scatter to rank order (utils.py:24-32,40); class masks
+        if (pass) {
+            const float xn = __fmul_rn(__fsub_rn(box.x, box.z), 0.5f), xx = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
+            const float yn = __fmul_rn(__fsub_rn(box.y, box.w), 0.5f), yx = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
+            scor[r] = make_float4(xn, xx, yn, yx);
+            sarea[r] = fabsf(__fmul_rn(__fsub_rn(xx, xn), __fsub_rn(yx, yn)));
+            smeta[r] = cls;
+        }
+        team_sync(bar_id, nthr);
+        const bool act = q < n;                                    // rank position q exists
+        const int qkey = act ? smeta[q] : 0;
+        const unsigned mm = __match_any_sync(FULL, act ? qkey : (0x7f000000 + lane));
+        const bool lead = act && (__ffs(mm) - 1) == lane;
+        if (lead) tbl[qkey * cc.TW + wt] = mm;
+        team_sync(bar_id, nthr);
+        // ---- D: suppression words against same-class predecessors (utils.py:108)
+        unsigned supp[kTeamWarpsMax];
+#pragma unroll
+        for (int w2 = 0; w2 < kTeamWarpsMax; ++w2) supp[w2] = 0u;
+        if (act) {
+            const unsigned *rowp = tbl + qkey * cc.TW;
+            const float4 qc = scor[q];
+            const float qa = sarea[q];
+#pragma unroll
+            for (int w2 = 0; w2 < kTeamWarpsMax; ++w2) {
+                if (w2 <= wt) {
+                    unsigned w = rowp[w2];
+                    if (w2 == wt) w &= lt_mask;
+                    while (w) {
+                        const int b = __ffs(w) - 1;
+                        w &= w - 1;
+                        if (suppresses(scor[32 * w2 + b], sarea[32 * w2 + b], qc, qa, cfg)) supp[w2] |= 1u << b;
+                    }
+                }
+            }
+        }
+        team_sync(bar_id, nthr);
+        if (lead) tbl[qkey * cc.TW + wt] = 0u;                     // leave the table zeroed
+        // ---- E: greedy keep flags, fixed point of keep[q] = !any(supp[q] & keep)
+        bool alive = act;
+        for (;;) {
+            const unsigned kb = __ballot_sync(FULL, alive);
+            if (lane == 0) kws[wt] = kb;
+            team_sync(bar_id, nthr);
+            unsigned sgot = 0u;
+#pragma unroll
+            for (int w2 = 0; w2 < kTeamWarpsMax; ++w2)
+                if (w2 <= wt) sgot |= supp[w2] & kws[w2];
+            const bool na = act && (sgot == 0u);
+            const bool ch = team_any(bar_id, nthr, na != alive);   // also: everybody has read kws
+            alive = na;
+            if (!ch) break;
+        }
+        // ---- F: output slots (kws holds the final keep words), rows in pick order (utils.py:112)
+        int K = 0, below = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kTeamWarpsMax; ++w2) {
+            if (w2 < cc.TW) {
+                const int k = __popc(kws[w2]);
+                if (w2 < wt) below += k;
+                K += k;
+            }
+        }
+        if (act) outpos[q] = alive ? below + __popc(kws[wt] & lt_mask) : -1;
+        team_sync(bar_id, nthr);
+        if (pass) {
+            const int pos = outpos[r];
+            if (pos >= 0) {
+                float2 *o = reinterpret_cast<float2 *>(out_boxes + (img * cfg.M + pos) * 6);
+                o[0] = make_float2(static_cast<float>(cls), conf);                    // utils.py:175
+                o[1] = make_float2(box.x, box.y);
+                o[2] = make_float2(box.z, box.w);
+                if (out_idx) out_idx[img * cfg.M + pos] = q;
+            }
+        }
+        if (q == 0) out_count[img] = K;
+        // the next image's first barrier separates its shared-memory writes (wcnt) from this image's reads
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // NMS over already decoded rows (n, M, 6): utils.py:79-114 as a batched call.
 // ------------------------------------------------------------------------------------------
 template <int NS>
@@ -1159,6 +1419,42 @@ static int launch_direct(const float *pred, int64_t n, NmsCfg cfg, float *out_bo
     return YH_OK;
 }
 
+// Big images, cooperative variant (decode_nms_coop_kernel): teams of ceil(M/32) warps per image.
+template <int CT, int BT>
+static int launch_coop(const float *pred, int64_t n, NmsCfg cfg, float *out_boxes, int *out_count, int *out_idx,
+                       cudaStream_t st, bool *launched)
+{
+    *launched = false;
+    const int64_t img_bytes = 4ll * cfg.M * cfg.D;
+    if (env_int("YH_COOP", 1) == 0 || reinterpret_cast<uintptr_t>(pred) % 16 != 0 || img_bytes % 16 != 0) return YH_OK;
+    CoopCfg cc;
+    cc.TW = (cfg.M + 31) / 32;
+    if (cc.TW > kTeamWarpsMax) return YH_OK;
+    cc.chunk_bytes = 32u * cfg.D * 4u;
+    cc.last_bytes = static_cast<uint32_t>(img_bytes - static_cast<int64_t>(cc.TW - 1) * cc.chunk_bytes);
+    if (cc.chunk_bytes % 16 != 0 || cc.last_bytes % 16 != 0) return YH_OK;
+    const int MPT = cc.TW * 32;
+    cc.team_bytes = (MPT * 16 + MPT * 4 + MPT * 4 + (MPT + 4) * 4 + MPT * 4 + 2 * kTeamWarpsMax * 4 + cfg.C * cc.TW * 4 + 15) & ~15;
+    cc.NTEAM = std::max(1, std::min(std::min(15, 31 / cc.TW), env_int("YH_COOP_TEAMS", 4)));
+    cc.ST = std::max(2, std::min(32, env_int("YH_COOP_STAGES", 10)));
+    auto need = [&](int teams, int stg) {
+        return static_cast<size_t>(stg) * cc.chunk_bytes + 2 * static_cast<size_t>(stg) * 8 + 16 + static_cast<size_t>(teams) * cc.team_bytes + 128;
+    };
+    while (cc.ST > 4 && need(cc.NTEAM, cc.ST) > 227 * 1024) --cc.ST;
+    while (cc.NTEAM > 1 && need(cc.NTEAM, cc.ST) > 227 * 1024) --cc.NTEAM;
+    while (cc.ST > 2 && need(cc.NTEAM, cc.ST) > 227 * 1024) --cc.ST;
+    if (need(cc.NTEAM, cc.ST) > 227 * 1024) return YH_OK;
+    cc.n = n;
+    const size_t smem = need(cc.NTEAM, cc.ST);
+    auto kern = decode_nms_coop_kernel<CT, BT>;
+    YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int grid = static_cast<int>(std::min<int64_t>(n, sm_count()));
+    kern<<<grid, 32 * (1 + cc.NTEAM * cc.TW), smem, st>>>(pred, cfg, cc, out_boxes, out_count, out_idx);
+    YH_LAUNCH_CHECK("decode_nms_coop_kernel");
+    *launched = true;
+    return YH_OK;
+}
+
 // Big images: chunked TMA ring + decode warps + NMS warps (decode_nms_big_kernel).  Returns
 // YH_OK with *launched = false when the shape does not qualify (the caller falls back to the direct kernel).
 template <int NS, int CT, int BT>
@@ -1249,7 +1545,10 @@ static int launch_fused(const float *pred, int64_t n, NmsCfg cfg, float *out_box
     // ---- images too large for the tile ring: chunked ring + warp specialisation ----
     if (done == 0 && img_bytes > 12 * 1024) {
         bool launched = false;
-        const int rc = launch_big<NS, CT, BT>(pred, n, cfg, out_boxes, out_count, out_idx, st, &launched);
+        int rc = launch_coop<CT, BT>(pred, n, cfg, out_boxes, out_count, out_idx, st, &launched);
+        if (rc != YH_OK) return rc;
+        if (launched) return YH_OK;
+        rc = launch_big<NS, CT, BT>(pred, n, cfg, out_boxes, out_count, out_idx, st, &launched);
         if (rc != YH_OK) return rc;
         if (launched) return YH_OK;
     }
