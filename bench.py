@@ -420,7 +420,7 @@ def other_configs(torch, dev, L, _lib, yu, sp):
     kept5 = int(cnt5.sum().item())
     gbs = (n5 * (4 * S5 * S5 * (C5 + 5 * B5) + 4) + 24 * kept5) / (ms * 1e-3) / 1e9
     out["cfg5_stress"] = {"images": n5, "images_per_s": n5 / (ms * 1e-3), "ms": ms, "GBps": gbs, "frac_hbm": gbs / peak,
-                          "kept_per_image": kept5 / n5, "kernel": "decode_nms_big_kernel<7,80,3>"}
+                          "kept_per_image": kept5 / n5, "kernel": "decode_nms_coop_kernel<80,3>"}
     del p5, boxes5, cnt5
     # cfg4: mAP over 5k images, single GPU (evaluator update + result)
     yt5 = F.synth_labels(5000, seed=11); mp5 = F.synth_map_pred(yt5)

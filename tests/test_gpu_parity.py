@@ -113,6 +113,20 @@ def test_decode_nms_paths_agree(dev, monkeypatch):
         ps = F.synth_stress(8)
         _check_nms(yu.decode_nms(_cuda(ps, dev), 80, 3, 0.5, 0.05, return_index=True), cport.decode_nms(ps, 80, 3, 0.5, 0.05), var + " stress")
         monkeypatch.delenv("YH_TMA"); monkeypatch.delenv(var)
+    # big images: cooperative team kernel (default, several team / ring geometries), the warp-specialised
+    # kernel behind it (YH_COOP=0, with and without the pair-parallel IoU phase), the direct kernel (YH_BIG=0)
+    ps = F.synth_stress(40)
+    pq = F.synth_quantised(24, 14, 3, 80, seed=9)
+    want_s, want_q = cport.decode_nms(ps, 80, 3, 0.5, 0.05), cport.decode_nms(pq, 80, 3, 0.5, 0.05)
+    for env in ({}, {"YH_COOP_TEAMS": "1"}, {"YH_COOP_TEAMS": "2", "YH_COOP_STAGES": "3"}, {"YH_COOP_STAGES": "16"},
+                {"YH_COOP": "0"}, {"YH_COOP": "0", "YH_BIG_PAIRS": "0"}, {"YH_COOP": "0", "YH_BIG_ND": "2", "YH_BIG_NN": "5"},
+                {"YH_COOP": "0", "YH_BIG": "0"}, {"YH_EXACT_DIV": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _check_nms(yu.decode_nms(_cuda(ps, dev), 80, 3, 0.5, 0.05, return_index=True), want_s, f"stress {env}")
+        _check_nms(yu.decode_nms(_cuda(pq, dev), 80, 3, 0.5, 0.05, return_index=True), want_q, f"stress-ties {env}")
+        for k in env:
+            monkeypatch.delenv(k)
     for T, W, ST in ((4, 8, 2), (16, 16, 2), (8, 8, 5), (8, 16, 3), (4, 24, 5), (8, 24, 8), (2, 24, 8)):
         monkeypatch.setenv("YH_TMA_T", str(T)); monkeypatch.setenv("YH_TMA_W", str(W)); monkeypatch.setenv("YH_TMA_STAGES", str(ST))
         _check_nms(yu.decode_nms(_cuda(p, dev), 20, 2, return_index=True), want, f"tma T{T} W{W} ST{ST}")
