@@ -470,3 +470,28 @@ def test_cfg4_full_size_map_5000_images(dev):
     got, ap = yu.mean_average_precision(_cuda(t_rows, dev), _cuda(p_rows, dev), 20, return_ap=True)
     assert abs(float(ev.result()) - float(want)) <= 1e-6 and abs(float(got) - float(want)) <= 1e-6
     np.testing.assert_allclose(ap.cpu().numpy(), want_ap, atol=1e-6)
+
+
+def test_big_image_edge_cases(dev):
+    """Shapes that take the cooperative team kernel (> 12 KB per image): empty images, one class with
+    identical boxes (longest suppression chain), all cells tied, other team widths (S=13 -> 6 warps,
+    S=16 -> 8 warps), single image, image counts around the team / CTA boundaries."""
+    from yolohot import utils as yu
+    S, B, C = 14, 3, 80
+    D = C + 5 * B
+    z = np.zeros((5, S, S, D), F32)
+    z[2, ..., C] = 0.05                                               # conf == threshold: strict >, nothing passes
+    _check_nms(yu.decode_nms(_cuda(z, dev), C, B, 0.5, 0.05, return_index=True), cport.decode_nms(z, C, B, 0.5, 0.05), "big zeros")
+    one = np.zeros((3, S, S, D), F32)
+    one[..., 7] = 1; one[..., C] = 0.9; one[..., C + 1:C + 5] = [0.5, 0.5, 0.2, 0.2]   # all tied, one class
+    one[1, ..., C] = np.linspace(0.06, 0.99, S * S).reshape(S, S)                       # strictly ordered chain
+    _check_nms(yu.decode_nms(_cuda(one, dev), C, B, 0.5, 0.05, return_index=True), cport.decode_nms(one, C, B, 0.5, 0.05), "big chain")
+    mixed = F.synth_stress(9)
+    mixed[4] = 0                                                      # an empty image between full ones
+    mixed[7, ..., :C] = 0; mixed[7, ..., 3] = 1                       # one image with a single class everywhere
+    _check_nms(yu.decode_nms(_cuda(mixed, dev), C, B, 0.5, 0.05, return_index=True), cport.decode_nms(mixed, C, B, 0.5, 0.05), "big mixed")
+    for (s_, b_, c_, thr) in ((13, 5, 7, 0.3), (16, 2, 4, 0.2), (12, 2, 40, 0.4), (10, 3, 100, 0.1)):
+        for n in (1, 3, 149, 600):
+            p = F.synth_quantised(n, s_, b_, c_, seed=n + s_) if n != 149 else F.synth_dense(n, s_, b_, c_, seed=s_)
+            _check_nms(yu.decode_nms(_cuda(p, dev), c_, b_, 0.45, thr, return_index=True),
+                       cport.decode_nms(p, c_, b_, 0.45, thr, nthreads=cport.num_threads()), f"S{s_} B{b_} C{c_} n{n}")
