@@ -399,9 +399,20 @@ def other_configs(torch, dev, L, _lib, yu, sp):
     ms, mn = timed(loss_round, 10)
     ms, mn = ms / len(sets), mn / len(sets)
     gbs = 3 * 4096 * IMG_IN / (ms * 1e-3) / 1e9
-    out["cfg3_loss_fwd_bwd_b4096"] = {"ms": ms, "ms_min": mn, "GBps": gbs, "frac_hbm": gbs / peak, "loss": float(terms[5]),
-                                      "l2": "8 rotating buffer sets (578 MB > L2), back-to-back launches"}
     del sets
+    # what the memory system delivers for a launch of THIS size: a plain device copy with the same traffic
+    half = 3 * 4096 * IMG_IN // 2
+    cs = [(torch.empty(half, dtype=torch.uint8, device=dev), torch.empty(half, dtype=torch.uint8, device=dev)) for _ in range(8)]
+
+    def copy_round():
+        for (a_, b_) in cs:
+            b_.copy_(a_)
+    cms, _ = timed(copy_round, 10)
+    cms /= len(cs)
+    out["cfg3_loss_fwd_bwd_b4096"] = {"ms": ms, "ms_min": mn, "GBps": gbs, "frac_hbm": gbs / peak, "loss": float(terms[5]),
+                                      "l2": "8 rotating buffer sets (578 MB > L2), back-to-back launches",
+                                      "device_copy_same_traffic_ms": cms, "frac_of_same_size_copy": cms / ms}
+    del cs
     # cfg5: stress S=14 B=3 C=80, conf threshold 0.05, ~80 % of the argmaxes in 4 dominant classes
     S5, B5, C5 = 14, 3, 80
     n5 = env_int("YH_BENCH_CFG5_IMAGES", 65_536)

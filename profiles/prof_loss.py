@@ -37,3 +37,22 @@ for g in (True, False):
         ts.append(e0.elapsed_time(e1) / 8)
     print("fwd+bwd" if g else "fwd    ", "us/launch mean %.1f min %.1f" % (1e3 * statistics.mean(ts), 1e3 * min(ts)),
           "GB/s %.0f" % ((3 if g else 2) * n * 5880 / min(ts) / 1e6), "loss", float(terms[5]))
+
+# size-matched copy: a plain device-to-device copy moving the same 72.25 MB of traffic (36.1 MB read + 36.1 MB
+# written), same rotation over 8 buffer sets - what the memory system delivers for a launch of this size
+nbytes = 3 * n * 5880 // 2
+srcs = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(8)]
+dsts = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(8)]
+for _ in range(3):
+    for a, b in zip(srcs, dsts):
+        b.copy_(a)
+ts = []
+for _ in range(10):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for a, b in zip(srcs, dsts):
+        b.copy_(a)
+    e1.record(); torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) / 8)
+print("copy    us/launch mean %.1f min %.1f" % (1e3 * statistics.mean(ts), 1e3 * min(ts)), "GB/s %.0f" % (2 * nbytes / min(ts) / 1e6),
+      "(same traffic as fwd+bwd)")
