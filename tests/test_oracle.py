@@ -191,3 +191,29 @@ def test_closed_form_grad_matches_autograd():
     # default mode takes the tie / clip masks from the float32 forward: same away from ties
     np.testing.assert_allclose(O.yolo_v1_loss_grad(yt, yp), p.grad.numpy(), rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(O.yolo_v1_loss_grad(*F.loss_demo(), 3, 2), G["loss_demo_grad"], rtol=1e-12, atol=1e-15)
+
+
+def test_division_free_iou_threshold_filter_is_exact():
+    """The NMS kernels decide `fl32(inter / den) < thr` (utils.py:108) without dividing whenever
+    |fl32(inter - fl32(thr * den))| > 2^-20 * fl32(thr * den) (csrc/yh_decode_nms.cu, suppresses()).
+    Emulated here in float32 NumPy on adversarial inputs (quotients within a few ulp of thr, and
+    quotients right at the edge of the 2^-20 band): wherever the filter decides, it decides like the division."""
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    eps = F32(2.0 ** -20)
+    for thr in (0.5, 0.45, 0.3, 0.25, 0.2, 0.05, 0.7, 0.999999, 1.0, 1e-3, 3.0):
+        t = F32(thr)
+        den = (rng.random(n, dtype=F32) * F32(2) + F32(1e-6)).astype(F32)
+        base = (den.astype(np.float64) * np.float64(t)).astype(F32)
+        inter = base.copy()
+        k = rng.integers(-4, 5, n).astype(np.int32)
+        inter[: n // 2] = (base[: n // 2].view(np.int32) + k[: n // 2]).view(F32)            # within 4 ulp of thr * den
+        edge = (1.0 + rng.choice([-1.0, 1.0], n - n // 2) * (2.0 ** -20) * (1.0 + 1e-3 * rng.standard_normal(n - n // 2)))
+        inter[n // 2:] = (base[n // 2:].astype(np.float64) * edge).astype(F32)              # at the edge of the band
+        inter[:1000] = rng.random(1000, dtype=F32) * den[:1000]                              # and ordinary values
+        ref_keep = (inter / den) < t                                                         # IEEE float32 division
+        p = t * den                                                                          # float32 product
+        d = inter - p                                                                        # float32 difference
+        decided = np.abs(d) > p * eps
+        assert decided[:1000].mean() > 0.99 and 0.2 < decided[n // 2:].mean() < 0.8          # both sides of the band hit
+        assert np.array_equal((d < 0)[decided], ref_keep[decided]), thr
