@@ -1112,6 +1112,7 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const float *_
     int *outpos = reinterpret_cast<int *>(tp);               tp += MPT * 4;
     int *wcnt = reinterpret_cast<int *>(tp);                 tp += kTeamWarpsMax * 4;
     unsigned *kws = reinterpret_cast<unsigned *>(tp);        tp += kTeamWarpsMax * 4;
+    unsigned *help = reinterpret_cast<unsigned *>(tp);       tp += MPT * (kTeamWarpsMax / 2) * 4;   // re-dealt words of phase D
     unsigned *tbl = reinterpret_cast<unsigned *>(tp);        // [C][TW]
     for (int i = q; i < cfg.C * cc.TW; i += nthr) tbl[i] = 0u;
     team_sync(bar_id, nthr);
@@ -1195,17 +1196,25 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const float *_
         const bool lead = act && (__ffs(mm) - 1) == lane;
         if (lead) tbl[qkey * cc.TW + wt] = mm;
         team_sync(bar_id, nthr);
-        // ---- D: suppression words against same-class predecessors (utils.py:108)
+        // ---- D: suppression words against same-class predecessors (utils.py:108).
+        //      Rank position q = 32 wt + lane has predecessors in words 0..wt of its class row, so the last
+        //      warp of a team has TW times the work of the first and the team would wait for it.  The words
+        //      are therefore re-dealt: warp wt > its mirror pw = TW-1-wt gives its lowest (wt - pw) / 2 words
+        //      to warp pw, whose lane l tests them for candidate 32 wt + l and hands the bits back through
+        //      shared memory (every warp then walks about (TW+1)/2 words).
         unsigned supp[kTeamWarpsMax];
 #pragma unroll
         for (int w2 = 0; w2 < kTeamWarpsMax; ++w2) supp[w2] = 0u;
+        const int pw = cc.TW - 1 - wt;                             // mirror warp
+        const int give = (wt > pw) ? ((wt - pw) >> 1) : 0;         // words 0..give-1 of this warp are done by warp pw
+        const int take = (pw > wt) ? ((pw - wt) >> 1) : 0;         // words 0..take-1 of warp pw are done here
         if (act) {
             const unsigned *rowp = tbl + qkey * cc.TW;
             const float4 qc = scor[q];
             const float qa = sarea[q];
 #pragma unroll
             for (int w2 = 0; w2 < kTeamWarpsMax; ++w2) {
-                if (w2 <= wt) {
+                if (w2 <= wt && w2 >= give) {
                     unsigned w = rowp[w2];
                     if (w2 == wt) w &= lt_mask;
                     while (w) {
@@ -1216,8 +1225,30 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const float *_
                 }
             }
         }
+        if (take > 0) {
+            const int q2 = 32 * pw + lane;                         // the mirror warp's candidate of this lane
+            if (q2 < n) {
+                const unsigned *rowp = tbl + smeta[q2] * cc.TW;
+                const float4 qc = scor[q2];
+                const float qa = sarea[q2];
+                for (int w2 = 0; w2 < take; ++w2) {                // all strictly below warp pw: no lane mask
+                    unsigned w = rowp[w2], hs = 0u;
+                    while (w) {
+                        const int b = __ffs(w) - 1;
+                        w &= w - 1;
+                        if (suppresses(scor[32 * w2 + b], sarea[32 * w2 + b], qc, qa, cfg)) hs |= 1u << b;
+                    }
+                    help[q2 * (kTeamWarpsMax / 2) + w2] = hs;
+                }
+            }
+        }
         team_sync(bar_id, nthr);
         if (lead) tbl[qkey * cc.TW + wt] = 0u;                     // leave the table zeroed
+        if (act) {
+#pragma unroll
+            for (int w2 = 0; w2 < kTeamWarpsMax / 2; ++w2)
+                if (w2 < give) supp[w2] = help[q * (kTeamWarpsMax / 2) + w2];
+        }
         // ---- E: greedy keep flags, fixed point of keep[q] = !any(supp[q] & keep)
         bool alive = act;
         for (;;) {
@@ -1434,7 +1465,8 @@ static int launch_coop(const float *pred, int64_t n, NmsCfg cfg, float *out_boxe
     cc.last_bytes = static_cast<uint32_t>(img_bytes - static_cast<int64_t>(cc.TW - 1) * cc.chunk_bytes);
     if (cc.chunk_bytes % 16 != 0 || cc.last_bytes % 16 != 0) return YH_OK;
     const int MPT = cc.TW * 32;
-    cc.team_bytes = (MPT * 16 + MPT * 4 + MPT * 4 + (MPT + 4) * 4 + MPT * 4 + 2 * kTeamWarpsMax * 4 + cfg.C * cc.TW * 4 + 15) & ~15;
+    cc.team_bytes = (MPT * 16 + MPT * 4 + MPT * 4 + (MPT + 4) * 4 + MPT * 4 + 2 * kTeamWarpsMax * 4 + MPT * (kTeamWarpsMax / 2) * 4 +
+                     cfg.C * cc.TW * 4 + 15) & ~15;
     cc.NTEAM = std::max(1, std::min(std::min(15, 31 / cc.TW), env_int("YH_COOP_TEAMS", 4)));
     cc.ST = std::max(2, std::min(32, env_int("YH_COOP_STAGES", 10)));
     auto need = [&](int teams, int stg) {
