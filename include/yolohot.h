@@ -37,6 +37,7 @@ extern "C" {
 #define YH_OK 0
 #define YH_ERR_ARG (-1)         /* null / shape / dtype / device / contiguity / alignment */
 #define YH_ERR_CUDA (-2)        /* a CUDA runtime call or launch failed */
+#define YH_ERR_NCCL (-3)        /* libnccl could not be loaded, or an NCCL call failed */
 #define YH_ERR_UNSUPPORTED (-4) /* configuration outside the compiled limits (e.g. S*S > 256) */
 
 #define YH_MAX_CELLS 256        /* S*S limit of the NMS kernels (8 candidate slots per lane) */
@@ -121,6 +122,30 @@ YH_API int yh_map_match(const float *true_rows, int64_t nt, const float *pred_ro
  * (out_map (1)). */
 YH_API int yh_map_reduce(const uint64_t *keys, const uint8_t *tp, int64_t nrec,
                   const int32_t *gt_per_class, int C, float *out_ap, float *out_map, void *stream);
+
+/* ---- multi-GPU exchange step of the mAP, single process driving all devices -------------
+ * (the Python mirror uses one process per GPU over torch.distributed instead, with
+ * the same result.)  Between yh_map_match on every shard and yh_map_reduce: the records of all
+ * devices are concatenated in device order (= image order) on every device, and the per-class
+ * ground-truth counts are summed.  NCCL is loaded at run time (libnccl.so.2 of the process).
+ * yh_comm_init_all: ncclCommInitAll over `devs` (NULL = 0..ndev-1).
+ * yh_map_allgather: keys[d] / tp[d] hold nrec[d] records on device d (nrec is a HOST array),
+ * gt_per_class[d] (C int32, device d) is all-reduced in place; out_keys[d] / out_tp[d] (device d,
+ * capacity out_capacity records) receive the concatenation; streams[d] (nullable) is device d's
+ * stream.  Asynchronous on those streams. */
+YH_API int yh_comm_init_all(int ndev, const int *devs, void **comm);
+YH_API int yh_comm_destroy(void *comm);
+YH_API int yh_map_allgather(void *comm, const uint64_t *const *keys, const uint8_t *const *tp, const int64_t *nrec,
+                     int32_t *const *gt_per_class, int C, uint64_t *const *out_keys, uint8_t *const *out_tp,
+                     int64_t out_capacity, void *const *streams);
+
+/* Device scratch (bytes) an operation allocates internally for n images / rows; informational. */
+#define YH_OP_DECODE_NMS 1
+#define YH_OP_DECODE_NMS_HOST 2
+#define YH_OP_LOSS 3
+#define YH_OP_MAP_MATCH 4
+#define YH_OP_MAP_REDUCE 5
+YH_API size_t yh_workspace_bytes(int op, int64_t n, int S, int B, int C);
 
 /* ---- callers either side of the path ------------------------ */
 

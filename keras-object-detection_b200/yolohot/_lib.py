@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("YH_LIB_PATH") or os.path.join(_HERE, "libyolohot.so")   # YH_LIB_PATH: A/B builds
 
-YH_OK, YH_ERR_ARG, YH_ERR_CUDA, YH_ERR_UNSUPPORTED = 0, -1, -2, -4
+YH_OK, YH_ERR_ARG, YH_ERR_CUDA, YH_ERR_NCCL, YH_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 YH_DTYPE_F16, YH_DTYPE_BF16 = 1, 2
 
 _lib = None
@@ -21,6 +21,7 @@ SYMBOLS = (
     "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_host", "yh_rows_append",
     "yh_loss", "yh_map_match", "yh_map_reduce",
     "yh_encode_labels", "yh_head_to_f32", "yh_pixel_boxes",
+    "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_workspace_bytes",
     "yh_iou_dl", "yh_decode_dl", "yh_nms_dl", "yh_decode_nms_dl", "yh_loss_dl",
 )
 
@@ -56,6 +57,11 @@ def lib():
     L.yh_encode_labels.argtypes = [vp, vp, i64, i, i, i, vp, vp, vp]
     L.yh_head_to_f32.argtypes = [vp, i, i64, vp, vp]
     L.yh_pixel_boxes.argtypes = [vp, vp, i64, i, i, i, vp, vp]
+    L.yh_comm_init_all.argtypes = [i, vp, vp]
+    L.yh_comm_destroy.argtypes = [vp]
+    L.yh_map_allgather.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, i64, vp]
+    L.yh_workspace_bytes.argtypes = [i, i64, i, i, i]
+    L.yh_workspace_bytes.restype = C.c_size_t
     L.yh_iou_dl.argtypes = [vp, vp, vp, vp]
     L.yh_decode_dl.argtypes = [vp, i, i, vp, vp]
     L.yh_nms_dl.argtypes = [vp, f, f, vp, vp, vp, vp]
@@ -63,7 +69,7 @@ def lib():
     L.yh_loss_dl.argtypes = [vp, vp, i, i, f, f, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(L, s)
-        if s not in ("yh_version", "yh_last_error", "yh_launch_count"):
+        if s not in ("yh_version", "yh_last_error", "yh_launch_count", "yh_workspace_bytes"):
             fn.restype = i
     _lib = L
     return L

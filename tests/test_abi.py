@@ -39,6 +39,13 @@ def test_argument_errors_need_no_gpu():
     assert L.yh_decode_nms(None, 4, 17, 2, 20, 0.5, 0.4, None, None, None, None) == _lib.YH_ERR_UNSUPPORTED
     assert L.yh_nms(None, 1, 300, 0.5, 0.4, None, None, None, None) == _lib.YH_ERR_UNSUPPORTED
     assert L.yh_loss(None, None, 10, 2, 20, 5.0, 0.5, None, None, None) == _lib.YH_ERR_ARG
+    assert L.yh_comm_init_all(0, None, None) == _lib.YH_ERR_ARG
+    assert L.yh_map_allgather(None, None, None, None, None, 20, None, None, 0, None) == _lib.YH_ERR_ARG
+    assert L.yh_comm_destroy(None) == _lib.YH_OK
+    assert L.yh_encode_labels(None, None, -1, 7, 2, 20, None, None, None) == _lib.YH_ERR_ARG
+    assert L.yh_head_to_f32(None, 7, 16, None, None) == _lib.YH_ERR_ARG
+    assert L.yh_pixel_boxes(None, None, 4, 0, 448, 448, None, None) == _lib.YH_ERR_ARG
+    assert L.yh_workspace_bytes(1, 1000, 7, 2, 20) == 0 and L.yh_workspace_bytes(3, 4096, 7, 2, 20) > 0
     with pytest.raises(ValueError):
         _lib.check(_lib.YH_ERR_ARG, "x")
     with pytest.raises(NotImplementedError):
