@@ -78,6 +78,16 @@ YH_API int yh_decode_nms(const float *pred, int64_t n, int S, int B, int C,
                   float iou_thr, float conf_thr,
                   float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, void *stream);
 
+/* Same with a score mode.  YH_SCORE_CONF is the reference (a cell's score is its best box
+ * confidence, utils.py:173,183-197).  YH_SCORE_CONF_X_PROB is an EXTENSION that the reference
+ * does not have: score = best box confidence x winning class probability (the class-specific
+ * score of the YOLO paper), used for the threshold, the order and the reported confidence. */
+#define YH_SCORE_CONF 0
+#define YH_SCORE_CONF_X_PROB 1
+YH_API int yh_decode_nms_ex(const float *pred, int64_t n, int S, int B, int C,
+                     float iou_thr, float conf_thr, int score_mode,
+                     float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, void *stream);
+
 /* Same, HOST buffers in and out (pageable or pinned): chunked H2D copy / kernel / D2H copy
  * pipelined on internal streams of device `device`; returns after the results are on the
  * host.  This is the call bench.py times for its end-to-end ("e2e") figure. */

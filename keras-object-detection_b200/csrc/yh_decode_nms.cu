@@ -31,6 +31,7 @@ struct NmsCfg {
     float inv_s;             // float32(1 / S)                         (utils.py:207)
     float iou_thr, conf_thr;
     int thr_fast;            // iou_thr is a positive normal float: the division-free filter of suppresses() applies
+    int score_mode;          // 0 = reference (best box confidence); 1 = confidence x class probability (extension)
     int ws_bytes;            // per-warp workspace bytes
     int tbl_rows;            // rows of the class table (C for fused, 32*NS for row input)
     int stage_bytes;         // direct kernel: per-warp staging buffer for one slot (32 cells), 0 = none
@@ -508,6 +509,7 @@ __device__ __forceinline__ void decode_cell(const float *__restrict__ p, const N
                                             int &cls, float &conf, float4 &box)
 {
     float bx, by, bw, bh;
+    float cbest;                                                   // the winning class score (score_mode 1 only)
     if constexpr (CT > 0 && BT > 0 && ((CT + 5 * BT) % 2 == 0)) {
         constexpr int D = CT + 5 * BT;
         float v[D];
@@ -523,6 +525,7 @@ __device__ __forceinline__ void decode_cell(const float *__restrict__ p, const N
 #pragma unroll
         for (int j = 1; j < CT; ++j)
             if (v[j] > best) { best = v[j]; cls = j; }            // first max (tf.argmax)
+        cbest = best;
         conf = v[CT]; bx = v[CT + 1]; by = v[CT + 2]; bw = v[CT + 3]; bh = v[CT + 4];
 #pragma unroll
         for (int b = 1; b < BT; ++b) {
@@ -555,6 +558,7 @@ __device__ __forceinline__ void decode_cell(const float *__restrict__ p, const N
             if (p[j] == best) cls = j;
         }
         if (p[8 * bb] == best) cls = 8 * bb;
+        cbest = best;
         int k = 0;
         conf = p[CT];
 #pragma unroll
@@ -572,6 +576,7 @@ __device__ __forceinline__ void decode_cell(const float *__restrict__ p, const N
             const float x = p[j];
             if (x > best) { best = x; cls = j; }
         }
+        cbest = best;
         int k = 0;
         conf = p[C];
         for (int b = 1; b < B; ++b) {
@@ -581,6 +586,9 @@ __device__ __forceinline__ void decode_cell(const float *__restrict__ p, const N
         const float *q = p + C + 5 * k;
         bx = q[1]; by = q[2]; bw = q[3]; bh = q[4];
     }
+    // Extension, NOT the reference (utils.py:173,183-197 scores a cell by its best box confidence only):
+    // score = confidence x winning class probability, the class-specific score of the YOLO paper
+    if (cfg.score_mode != 0) conf = __fmul_rn(conf, cbest);
     box.x = __fmul_rn(cfg.inv_s, __fadd_rn(bx, colf));             // utils.py:207 (column)
     box.y = __fmul_rn(cfg.inv_s, __fadd_rn(by, rowf));             // utils.py:208 (row)
     box.z = bw;
@@ -1406,7 +1414,7 @@ static int fill_cfg(NmsCfg &cfg, int S, int B, int C, float iou_thr, float conf_
     cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
     cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
     cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr;
-    cfg.ws_bytes = 0; cfg.tbl_rows = C; cfg.stage_bytes = 0;
+    cfg.ws_bytes = 0; cfg.tbl_rows = C; cfg.stage_bytes = 0; cfg.score_mode = 0;
     set_thr(cfg);
     return YH_OK;
 }
@@ -1593,11 +1601,13 @@ static int launch_fused(const float *pred, int64_t n, NmsCfg cfg, float *out_box
 }
 
 int decode_nms_device(const float *pred, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
-                      float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, cudaStream_t st)
+                      float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, cudaStream_t st, int score_mode)
 {
     NmsCfg cfg;
     int rc = fill_cfg(cfg, S, B, C, iou_thr, conf_thr);
     if (rc != YH_OK) return rc;
+    YH_REQUIRE(score_mode == YH_SCORE_CONF || score_mode == YH_SCORE_CONF_X_PROB, "decode_nms: unknown score_mode %d", score_mode);
+    cfg.score_mode = score_mode;
     YH_REQUIRE(n >= 0, "decode_nms: n < 0");
     if (n == 0) return YH_OK;
     YH_REQUIRE(pred && out_boxes && out_count, "decode_nms: null pointer");
@@ -1646,7 +1656,14 @@ extern "C" int yh_decode_nms(const float *pred, int64_t n, int S, int B, int C, 
                              float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, void *stream)
 {
     return decode_nms_device(pred, n, S, B, C, iou_thr, conf_thr, out_boxes, out_count, out_keep_idx,
-                             static_cast<cudaStream_t>(stream));
+                             static_cast<cudaStream_t>(stream), YH_SCORE_CONF);
+}
+
+extern "C" int yh_decode_nms_ex(const float *pred, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
+                                int score_mode, float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, void *stream)
+{
+    return decode_nms_device(pred, n, S, B, C, iou_thr, conf_thr, out_boxes, out_count, out_keep_idx,
+                             static_cast<cudaStream_t>(stream), score_mode);
 }
 
 extern "C" int yh_nms(const float *boxes, int64_t n, int M, float iou_thr, float conf_thr, float *out_boxes,
@@ -1663,7 +1680,7 @@ extern "C" int yh_nms(const float *boxes, int64_t n, int M, float iou_thr, float
                "nms: boxes and out_boxes must be 8-byte aligned");
     NmsCfg cfg;
     cfg.S = 0; cfg.B = 0; cfg.C = 0; cfg.M = M; cfg.D = 6; cfg.inv_s = 0.f;
-    cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.stage_bytes = 0;
+    cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.stage_bytes = 0; cfg.score_mode = 0;
     set_thr(cfg);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (pick_ns(M)) {
@@ -1683,7 +1700,7 @@ extern "C" int yh_decode(const float *pred, int64_t n, int S, int B, int C, floa
     cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
     cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
     cfg.iou_thr = cfg.conf_thr = 0.f; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.stage_bytes = 0;
-    cfg.thr_fast = 0;
+    cfg.thr_fast = 0; cfg.score_mode = 0;
     if (n == 0) return YH_OK;
     YH_REQUIRE(pred && out_boxes, "decode: null pointer");
     YH_REQUIRE(reinterpret_cast<uintptr_t>(out_boxes) % 8 == 0, "decode: out_boxes must be 8-byte aligned");

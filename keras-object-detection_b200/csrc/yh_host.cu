@@ -13,7 +13,7 @@
 namespace yh {
 
 int decode_nms_device(const float *pred, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
-                      float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, cudaStream_t st);
+                      float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, cudaStream_t st, int score_mode);
 
 constexpr int kSlots = 3;
 
@@ -90,7 +90,7 @@ extern "C" int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int 
         cudaStream_t st = cx.st[s];
         YH_CUDA(cudaMemcpyAsync(cx.d_in[s], pred_host + lo * M * D, cnt * img_in, cudaMemcpyHostToDevice, st));
         rc = decode_nms_device(cx.d_in[s], cnt, S, B, C, iou_thr, conf_thr, cx.d_boxes[s], cx.d_count[s],
-                               out_keep_idx_host ? cx.d_idx[s] : nullptr, st);
+                               out_keep_idx_host ? cx.d_idx[s] : nullptr, st, YH_SCORE_CONF);
         if (rc != YH_OK) break;
         YH_CUDA(cudaMemcpyAsync(out_boxes_host + lo * M * 6, cx.d_boxes[s], cnt * img_boxes, cudaMemcpyDeviceToHost, st));
         YH_CUDA(cudaMemcpyAsync(out_count_host + lo, cx.d_count[s], cnt * 4, cudaMemcpyDeviceToHost, st));

@@ -123,14 +123,22 @@ def non_max_suppression_2(boxes, iou_threshold=0.5, conf_threshold=0.4):
 
 
 def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_threshold=0.4,
-               return_index=False, out=None, grid=None):
+               return_index=False, out=None, grid=None, score_mode="conf"):
     """Fused, batched loop body of utils.py:470-480 (decode + per-image NMS).
 
     Returns (boxes (N,S*S,6), count (N,) int32[, keep_idx (N,S*S) int32]): the first count[i]
     rows of image i are its kept rows in pick order; rows past that are unspecified unless
     `out` buffers were zeroed by the caller.  Host array-likes go through the pipelined
-    host entry point (yh_decode_nms_host) and come back as NumPy."""
+    host entry point (yh_decode_nms_host) and come back as NumPy.
+
+    score_mode="conf" is the reference (a cell's score is its best box confidence).
+    score_mode="conf_x_prob" is an extension the reference does not have: confidence x winning
+    class probability decides the threshold, the order and the reported confidence."""
     L = _lib.lib()
+    if score_mode not in ("conf", "conf_x_prob"):
+        raise ValueError(f"decode_nms: score_mode must be 'conf' or 'conf_x_prob', got {score_mode!r}")
+    if score_mode != "conf" and (isinstance(predictions, np.ndarray) or not (isinstance(predictions, torch.Tensor) or hasattr(predictions, "__dlpack__"))):
+        predictions = torch.from_numpy(np.ascontiguousarray(np.asarray(predictions, dtype=np.float32))).cuda()
     if not isinstance(predictions, torch.Tensor) and not hasattr(predictions, "__dlpack__") or isinstance(predictions, np.ndarray):
         require_cuda()
         p = np.ascontiguousarray(np.asarray(predictions, dtype=np.float32))
@@ -160,9 +168,14 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
         cnt = torch.empty((n,), dtype=torch.int32, device=p.device)
         kidx = torch.empty((n, S * S), dtype=torch.int32, device=p.device) if return_index else None
     with torch.cuda.device(p.device):
-        hp, hb, hc, hk = DL(p), DL(boxes), DL(cnt), dl(kidx)
-        _lib.check(L.yh_decode_nms_dl(hp.ptr, int(num_boxes), int(num_classes), float(iou_threshold),
-                                      float(conf_threshold), hb.ptr, hc.ptr, ptr(hk), stream_ptr(p.device)), "decode_nms")
+        if score_mode == "conf":
+            hp, hb, hc, hk = DL(p), DL(boxes), DL(cnt), dl(kidx)
+            _lib.check(L.yh_decode_nms_dl(hp.ptr, int(num_boxes), int(num_classes), float(iou_threshold),
+                                          float(conf_threshold), hb.ptr, hc.ptr, ptr(hk), stream_ptr(p.device)), "decode_nms")
+        else:
+            _lib.check(L.yh_decode_nms_ex(p.data_ptr(), n, S, int(num_boxes), int(num_classes), float(iou_threshold),
+                                          float(conf_threshold), 1, boxes.data_ptr(), cnt.data_ptr(),
+                                          kidx.data_ptr() if kidx is not None else None, stream_ptr(p.device)), "decode_nms")
     if return_index:
         return give_back(boxes, kind), give_back(cnt, kind), give_back(kidx, kind)
     return give_back(boxes, kind), give_back(cnt, kind)

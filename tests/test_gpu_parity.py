@@ -495,3 +495,23 @@ def test_big_image_edge_cases(dev):
             p = F.synth_quantised(n, s_, b_, c_, seed=n + s_) if n != 149 else F.synth_dense(n, s_, b_, c_, seed=s_)
             _check_nms(yu.decode_nms(_cuda(p, dev), c_, b_, 0.45, thr, return_index=True),
                        cport.decode_nms(p, c_, b_, 0.45, thr, nthreads=cport.num_threads()), f"S{s_} B{b_} C{c_} n{n}")
+
+
+def test_score_mode_extension(dev):
+    """score_mode='conf_x_prob' (not in the reference): conf x winning class probability drives the
+    threshold, the order and the reported confidence.  Checked against the oracle's NMS run on decoded
+    rows whose confidence column was multiplied by the float32 class maximum."""
+    from yolohot import utils as yu
+    for (gen, n, S, B, C, it, ct) in ((F.synth_dense, 300, 7, 2, 20, 0.5, 0.25), (F.synth_stress, 20, 14, 3, 80, 0.5, 0.3)):
+        p = gen(n, S, B, C)
+        rows = O.decode_predictions(p, C, B)
+        rows[..., 1] = (rows[..., 1] * p[..., :C].max(-1).reshape(n, -1)).astype(F32)
+        got_b, got_c = yu.decode_nms(_cuda(p, dev), C, B, it, ct, score_mode="conf_x_prob")
+        got_b, got_c = got_b.cpu().numpy(), got_c.cpu().numpy()
+        for i in range(n):
+            want = O.non_max_suppression(rows[i], it, ct)
+            assert got_c[i] == len(want) and np.array_equal(got_b[i, :len(want)], want), i
+    ref_b, ref_c = yu.decode_nms(_cuda(p, dev), C, B, it, ct)                    # default stays the reference
+    _check_nms((ref_b, ref_c, yu.decode_nms(_cuda(p, dev), C, B, it, ct, return_index=True)[2]), cport.decode_nms(p, C, B, it, ct), "default")
+    with pytest.raises(ValueError):
+        yu.decode_nms(_cuda(p, dev), C, B, score_mode="prob")
