@@ -15,9 +15,10 @@
 //   E  greedy keep flags by fixed-point iteration on ballots (exact: position q depends
 //      only on positions < q, so the iteration converges to the sequential result)
 //   F  kept rows are written in rank order; count per image
-// The fast path stages image tiles in shared memory with cp.async.bulk (TMA) through an
-// mbarrier ring filled by a producer warp; a direct-from-global kernel covers the tail,
-// unaligned inputs and grids too large for the ring.
+// Kernels: decode_nms_tma_kernel (images <= 12 KB: tiles of whole images through a TMA ring, one warp
+// per image), decode_nms_coop_kernel (bigger images: 32-cell chunks through a TMA ring, a team of
+// warps per image, one thread per cell), decode_nms_direct_kernel (tails, unaligned inputs, anything
+// else), nms_rows_kernel / decode_kernel / iou_kernel (the reference's separate calls).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -34,7 +35,6 @@ struct NmsCfg {
     int score_mode;          // 0 = reference (best box confidence); 1 = confidence x class probability (extension)
     int ws_bytes;            // per-warp workspace bytes
     int tbl_rows;            // rows of the class table (C for fused, 32*NS for row input)
-    int stage_bytes;         // direct kernel: per-warp staging buffer for one slot (32 cells), 0 = none
 };
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -61,20 +61,6 @@ struct WarpWs {
     int *outpos;      //          aliased afterwards: output slot of rank position q, -1 = suppressed
     float *cclsf;     // [MP]  compact float classes          (kFloatCls only)
     unsigned *tbl;    // [tbl_rows * NS] class key -> lanes holding that class, per slot
-    unsigned *supp_s; // [MP * NS] suppression bit rows in shared memory (pair-parallel phase D), else nullptr
-    unsigned char *list;   // [MP]  rank positions of the members of one class, in rank order
-
-    // Bit rows are triangular: rank position q = lane + 32 t only has predecessors in words 0..t, so
-    // its row holds t + 1 words; rows of slot t start at word 32 * t(t+1)/2.
-    static constexpr int kSuppWords = 16 * NS * (NS + 1);
-    __host__ __device__ static int supp_row(int q) { const int t = q >> 5; return 16 * t * (t + 1) + (q & 31) * (t + 1); }
-    // extra bytes behind bytes(tbl_rows) when the pair-parallel phase D is used
-    __host__ __device__ static int pair_bytes() { return kSuppWords * 4 + MP; }
-    __device__ void enable_pairs(unsigned char *p)
-    {
-        supp_s = reinterpret_cast<unsigned *>(p);
-        list = p + kSuppWords * 4;
-    }
 
     __host__ __device__ static int bytes(int tbl_rows)
     {
@@ -95,8 +81,6 @@ struct WarpWs {
             cclsf = reinterpret_cast<float *>(p);  p += MP * 4;
         }
         tbl = reinterpret_cast<unsigned *>(p);
-        supp_s = nullptr;
-        list = nullptr;
     }
 };
 
@@ -324,112 +308,6 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
             if (lo) { cur_lo ^= bit; s_lo |= sb; } else { cur_hi ^= bit; s_hi |= sb; }
         }
         if (on1) { supp[1][0] = s_lo; supp[1][1] = s_hi; } else { supp[0][0] = s_lo; }
-    } else if (ws.supp_s != nullptr) {
-        // Pair-parallel phase D.  With lane = candidate, a warp runs max-over-lanes trips and most
-        // lanes idle (few candidates have many same-class predecessors).  Instead, every class with
-        // more than kSmall members is processed on its own: its members are listed in rank order and
-        // the k(k-1)/2 (earlier, later) pairs are dealt out to the 32 lanes, one IoU test per lane
-        // and step, hits OR-ed into the later box's bit row in shared memory.  Small classes keep
-        // the lane = candidate loop (at most kSmall - 1 tests per candidate).
-        constexpr int kSmall = 5;
-        {
-            uint4 *z = reinterpret_cast<uint4 *>(ws.supp_s);
-            const int nz = (16 * NT * (NT + 1) + 3) >> 2;          // rows of slots 0..NT-1
-            for (int i = lane; i < nz; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        int jq[NS], kq[NS];                        // index within the class (rank order) / class size
-#pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            jq[t] = 0; kq[t] = 0;
-            if (t < NT && ((act_m >> t) & 1u)) {
-                const unsigned *row = ws.tbl + qkey[t] * NS;
-#pragma unroll
-                for (int t2 = 0; t2 < NS; ++t2) {
-                    if (t2 < NT) {
-                        const unsigned w = row[t2];
-                        kq[t] += __popc(w);
-                        if (t2 < t) jq[t] += __popc(w);
-                        if (t2 == t) jq[t] += __popc(w & lt_mask);
-                    }
-                }
-            }
-        }
-        __syncwarp();                              // rows are zeroed before anybody ORs into them
-        // small classes: lane = candidate
-#pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            if (t < NT && ((act_m >> t) & 1u) && kq[t] <= kSmall && jq[t] > 0) {
-                const unsigned *row = ws.tbl + qkey[t] * NS;
-                const int q = lane + 32 * t;
-                const float4 qc = ws.scor[q];
-                const float qa = ws.sarea[q];
-                for (int t2 = 0; t2 <= t; ++t2) {
-                    unsigned w = row[t2];
-                    if (t2 == t) w &= lt_mask;
-                    unsigned acc = 0u;
-                    while (w) {
-                        const int b = __ffs(w) - 1;
-                        w &= w - 1;
-                        if (suppresses(ws.scor[32 * t2 + b], ws.sarea[32 * t2 + b], qc, qa, cfg)) acc |= 1u << b;
-                    }
-                    if (acc) ws.supp_s[ws.supp_row(q) + t2] = acc;
-                }
-            }
-        }
-        // big classes, one after the other (warp-uniform loop over their first members)
-#pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            if (t >= NT) continue;
-            unsigned bm = __ballot_sync(FULL, ((act_m >> t) & 1u) && jq[t] == 0 && kq[t] > kSmall);
-            while (bm) {
-                const int src = __ffs(bm) - 1;
-                bm &= bm - 1;
-                const int key_c = __shfl_sync(FULL, qkey[t], src);
-                const int k = __shfl_sync(FULL, kq[t], src);
-#pragma unroll
-                for (int u = 0; u < NS; ++u)
-                    if (u < NT && ((act_m >> u) & 1u) && qkey[u] == key_c) ws.list[jq[u]] = static_cast<unsigned char>(lane + 32 * u);
-                __syncwarp();
-                // The k(k-1)/2 pairs as a folded triangle: virtual row v joins the predecessors of member
-                // k-1-v (x < k-1-v) with those of member v, k-1 entries in all; pair e sits at row
-                // e / (k-1), column e % (k-1) - closed form, every lane busy, two pairs per trip so that
-                // two independent load -> test chains are in flight.
-                const int P = (k * (k - 1)) >> 1;
-                const int km1 = k - 1;
-                const float inv = 1.0f / static_cast<float>(km1);
-                auto pair_of = [&](int e, int &a, int &b) {
-                    int v = static_cast<int>(static_cast<float>(e) * inv);     // e < 2^15: off by at most one
-                    int x = e - v * km1;
-                    if (x < 0) { x += km1; --v; }
-                    if (x >= km1) { x -= km1; ++v; }
-                    const int b1 = km1 - v;
-                    const bool first = x < b1;
-                    b = first ? b1 : v;
-                    a = first ? x : x - b1;
-                };
-                for (int e = lane; e < P; e += 64) {
-                    const bool two = (e + 32) < P;
-                    int a, b, a2, b2;
-                    pair_of(e, a, b);
-                    pair_of(two ? e + 32 : e, a2, b2);
-                    const int pa = ws.list[a], pb = ws.list[b];
-                    const int pa2 = ws.list[a2], pb2 = ws.list[b2];
-                    const bool s1 = suppresses(ws.scor[pa], ws.sarea[pa], ws.scor[pb], ws.sarea[pb], cfg);
-                    const bool s2 = suppresses(ws.scor[pa2], ws.sarea[pa2], ws.scor[pb2], ws.sarea[pb2], cfg);
-                    if (s1) atomicOr(ws.supp_s + ws.supp_row(pb) + (pa >> 5), 1u << (pa & 31));
-                    if (s2 && two) atomicOr(ws.supp_s + ws.supp_row(pb2) + (pa2 >> 5), 1u << (pa2 & 31));
-                }
-                __syncwarp();                      // the list is rewritten by the next class
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            if (t < NT && ((act_m >> t) & 1u)) {
-#pragma unroll
-                for (int t2 = 0; t2 <= t; ++t2) supp[t][t2] = ws.supp_s[16 * t * (t + 1) + lane * (t + 1) + t2];
-            }
-        }
     } else {
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
@@ -596,38 +474,12 @@ __device__ __forceinline__ void decode_cell(const float *__restrict__ p, const N
 }
 
 // ------------------------------------------------------------------------------------------
-// Direct kernel: one warp per image, no CTA-level cooperation.  Covers tails, inputs that are
-// only 8-byte aligned, and images too large for the TMA ring (e.g. S=14, B=3, C=80: 74 KB).
-// Slot t of an image (cells 32t .. 32t+31) is one contiguous chunk of 32*D floats: the warp copies it
-// into its own shared-memory staging buffer with coalesced vector loads, then every lane decodes its
-// cell from shared memory (row stride D words).  Reading the cells straight from global memory would
-// cost one L1 wavefront per lane per load (32 different lines per instruction).
-// Any shape (S*S <= 32 NS), any alignment >= 4 B.
+// Direct kernel: one warp per image, cells read straight from global memory / L1, no CTA-level
+// cooperation.  Covers tails, inputs that are only 8-byte aligned and every shape the ring kernels
+// cannot take.  Any shape (S*S <= 32 NS), any alignment >= 4 B.  (Two staged variants - per-slot LDG
+// staging and a per-warp cp.async.bulk double buffer - were measured slower, because they leave
+// fewer resident warps for what is a serial chain per warp, and were removed.)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_copy_to_smem(float *__restrict__ dst, const float *__restrict__ src, int nfl, int lane)
-{
-    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-    if ((a & 15) == 0) {
-        const int n4 = nfl >> 2;
-        const float4 *s4 = reinterpret_cast<const float4 *>(src);
-        float4 *d4 = reinterpret_cast<float4 *>(dst);
-        int i = lane;
-#pragma unroll 4
-        for (; i < n4; i += 32) d4[i] = __ldcs(s4 + i);
-        for (int j = (n4 << 2) + lane; j < nfl; j += 32) dst[j] = __ldcs(src + j);
-    } else if ((a & 7) == 0) {
-        const int n2 = nfl >> 1;
-        const float2 *s2 = reinterpret_cast<const float2 *>(src);
-        float2 *d2 = reinterpret_cast<float2 *>(dst);
-#pragma unroll 4
-        for (int i = lane; i < n2; i += 32) d2[i] = __ldcs(s2 + i);
-        for (int j = (n2 << 1) + lane; j < nfl; j += 32) dst[j] = __ldcs(src + j);
-    } else {
-#pragma unroll 4
-        for (int j = lane; j < nfl; j += 32) dst[j] = __ldcs(src + j);
-    }
-}
-
 template <int NS, int CT, int BT>
 __global__ void __launch_bounds__(512) decode_nms_direct_kernel(const float *__restrict__ pred, int64_t n, NmsCfg cfg,
                                                                 float *__restrict__ out_boxes,
@@ -635,9 +487,7 @@ __global__ void __launch_bounds__(512) decode_nms_direct_kernel(const float *__r
 {
     extern __shared__ uint4 smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    unsigned char *mine = reinterpret_cast<unsigned char *>(smem_raw) + static_cast<size_t>(warp) * (cfg.ws_bytes + cfg.stage_bytes);
-    WarpWs<NS, false> ws(mine);
-    float *stage = reinterpret_cast<float *>(mine + cfg.ws_bytes);
+    WarpWs<NS, false> ws(reinterpret_cast<unsigned char *>(smem_raw) + static_cast<size_t>(warp) * cfg.ws_bytes);
     for (int i = lane; i < cfg.tbl_rows * NS; i += 32) ws.tbl[i] = 0u;
     __syncwarp();
 
@@ -659,92 +509,7 @@ __global__ void __launch_bounds__(512) decode_nms_direct_kernel(const float *__r
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
             conf[t] = -INFINITY; cls[t] = 0; box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int cells = min(32, cfg.M - 32 * t);
-            if (cells > 0) {
-                if (cfg.stage_bytes > 0) {
-                    __syncwarp();                                  // the previous slot has been consumed
-                    warp_copy_to_smem(stage, base + 32 * t * cfg.D, cells * cfg.D, lane);
-                    __syncwarp();
-                    if (valid[t]) decode_cell<0, 0>(stage + lane * cfg.D, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
-                } else if (valid[t]) {                             // straight from global / L1 (more resident warps)
-                    decode_cell<CT, BT>(base + (lane + 32 * t) * cfg.D, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
-                }
-            }
-        }
-        const int K = nms_warp<NS, false>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
-                                          out_idx ? out_idx + img * cfg.M : nullptr);
-        if (lane == 0) out_count[img] = K;
-    }
-}
-
-// Same work split, but every warp runs its own two-deep cp.async.bulk (TMA) pipeline over the flat
-// sequence of its (image, slot) chunks: chunk c lands in buffer c & 1 and completes mbarrier c & 1;
-// chunk c + 1 is issued as soon as chunk c - 1 has been decoded, so the first slot of the NEXT image
-// streams in while the NMS phases of the current one run.  Needs 16-byte aligned chunks.
-template <int NS, int CT, int BT>
-__global__ void __launch_bounds__(512) decode_nms_warp_tma_kernel(const float *__restrict__ pred, int64_t n, NmsCfg cfg,
-                                                                  float *__restrict__ out_boxes,
-                                                                  int *__restrict__ out_count, int *__restrict__ out_idx)
-{
-    extern __shared__ uint4 smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const int per_warp = cfg.ws_bytes + 2 * cfg.stage_bytes + 16;
-    unsigned char *mine = reinterpret_cast<unsigned char *>(smem_raw) + static_cast<size_t>(warp) * per_warp;
-    WarpWs<NS, false> ws(mine);
-    unsigned char *stage = mine + cfg.ws_bytes;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(mine + cfg.ws_bytes + 2 * cfg.stage_bytes);
-    for (int i = lane; i < cfg.tbl_rows * NS; i += 32) ws.tbl[i] = 0u;
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-
-    float colf[NS], rowf[NS];
-    bool valid[NS];
-#pragma unroll
-    for (int t = 0; t < NS; ++t) {
-        const int cell = lane + 32 * t;
-        valid[t] = cell < cfg.M;
-        rowf[t] = static_cast<float>(cell / cfg.S);
-        colf[t] = static_cast<float>(cell % cfg.S);
-    }
-    const int slots = (cfg.M + 31) >> 5;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * wpb;
-    const int64_t img0 = static_cast<int64_t>(blockIdx.x) * wpb + warp;
-    const uint64_t pol = l2_evict_first_policy();
-    const uint32_t slot_bytes = 32u * cfg.D * 4u;
-
-    // chunk (image, t) -> issue into buffer `b`
-    auto issue = [&](int64_t img, int t, int b) {
-        const uint32_t bytes = static_cast<uint32_t>(min(32, cfg.M - 32 * t)) * cfg.D * 4u;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the buffer vs. the async write
-        mbar_arrive_expect_tx(bar + b, bytes);
-        bulk_g2s(stage + static_cast<size_t>(b) * cfg.stage_bytes,
-                 reinterpret_cast<const unsigned char *>(pred + img * cfg.M * cfg.D) + static_cast<size_t>(t) * slot_bytes, bytes,
-                 bar + b, pol);
-    };
-    if (img0 < n && lane == 0) issue(img0, 0, 0);
-    uint32_t c = 0;                                               // running chunk counter of this warp
-    for (int64_t img = img0; img < n; img += stride) {
-        float conf[NS];
-        float4 box[NS];
-        int cls[NS];
-#pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            conf[t] = -INFINITY; cls[t] = 0; box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t < slots) {
-                __syncwarp();                                      // chunk c - 1 (other buffer) has been consumed
-                if (lane == 0) {                                   // prefetch chunk c + 1 into the other buffer
-                    if (t + 1 < slots) issue(img, t + 1, (c + 1) & 1);
-                    else if (img + stride < n) issue(img + stride, 0, (c + 1) & 1);
-                }
-                mbar_wait(bar + (c & 1), (c >> 1) & 1);
-                const float *cellp = reinterpret_cast<const float *>(stage + static_cast<size_t>(c & 1) * cfg.stage_bytes) + lane * cfg.D;
-                if (valid[t]) decode_cell<0, 0>(cellp, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
-                ++c;
-            }
+            if (valid[t]) decode_cell<CT, BT>(base + (lane + 32 * t) * cfg.D, cfg, colf[t], rowf[t], cls[t], conf[t], box[t]);
         }
         const int K = nms_warp<NS, false>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
                                           out_idx ? out_idx + img * cfg.M : nullptr);
@@ -845,166 +610,6 @@ __global__ void __launch_bounds__(800, 1) decode_nms_tma_kernel(const float *__r
         if (lane == 0) out_count[img] = K;
         s += G;
         while (s >= tc.ST) { s -= tc.ST; ph ^= 1u; }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Big-image kernel (images > 12 KB, e.g. S=14, B=3, C=80: 74,480 B): persistent CTAs, three warp
-// roles connected by mbarrier queues, so that no warp ever waits on global-memory latency:
-//   warp 0            producer: cp.async.bulk (TMA) of 32-cell chunks (32*D*4 B) of the CTA's images,
-//                     in order, into an ST-deep shared-memory ring
-//   warps 1..ND       decode warps: chunk c of the CTA's flat chunk sequence goes to warp c % ND; lane
-//                     = cell; the decoded (conf, class, box) of the cell is written to the input area
-//                     of the NMS warp that owns the image, then the ring stage is released
-//   warps ND+1..      NMS warps: image i of the CTA goes to warp i % NN; it pulls the decoded image
-//                     into registers, frees its input area for the next image and runs phases B..F
-// Queues: full/empty per ring stage; in_full (count = chunks per image) / in_empty per NMS warp.
-// mbarrier parity waits are only meaningful while the waiter is within one phase of the barrier,
-// which the host configuration guarantees: ST is a multiple of ND, so a stage (c % ST) is always
-// consumed by the same decode warp (c % ND) and that warp's waits on it are strictly sequential; ND
-// <= chunks per image, so every decode warp holds a chunk of every image and none can run a whole
-// round ahead of an NMS warp's input area; in_full[w] is only waited on by NMS warp w.
-// ------------------------------------------------------------------------------------------
-struct BigCfg {
-    int ST, ND, NN;         // ring stages, decode warps, NMS warps
-    int slots;              // chunks per image = ceil(M / 32)
-    uint32_t chunk_bytes;   // 32 * D * 4
-    uint32_t last_bytes;    // bytes of the last chunk of an image
-    int in_bytes;           // per NMS warp: decoded image area (conf, cls, box per cell)
-    int pairs, pair_bytes;  // pair-parallel phase D (NS > 2): extra per-NMS-warp bytes (bit rows + class list)
-    int64_t n;
-};
-
-template <int NS, int CT, int BT>
-__global__ void __launch_bounds__(512, 1) decode_nms_big_kernel(const float *__restrict__ pred, NmsCfg cfg, BigCfg bc,
-                                                                float *__restrict__ out_boxes, int *__restrict__ out_count,
-                                                                int *__restrict__ out_idx)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int MP = 32 * NS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *ring = smem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(bc.ST) * bc.chunk_bytes);
-    uint64_t *empty = full + bc.ST;
-    uint64_t *in_full = empty + bc.ST;
-    uint64_t *in_empty = in_full + bc.NN;
-    unsigned char *areas = reinterpret_cast<unsigned char *>(in_empty + bc.NN);
-    areas += (16 - (reinterpret_cast<uintptr_t>(areas) & 15)) & 15;
-    const int per_nms = cfg.ws_bytes + bc.in_bytes + bc.pair_bytes;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < bc.ST; ++s) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
-        }
-        for (int w = 0; w < bc.NN; ++w) {
-            mbar_init(in_full + w, bc.slots);
-            mbar_init(in_empty + w, 1);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    // images of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int64_t my_imgs = (bc.n > blockIdx.x) ? (bc.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t n_chunks = my_imgs * bc.slots;
-    const int64_t img_bytes = 4ll * cfg.M * cfg.D;
-
-    if (warp == 0) {                                               // ---- producer
-        if (lane == 0) {
-            const uint64_t pol = l2_evict_first_policy();
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(pred);
-            int s = 0, t = 0;
-            uint32_t ph = 0;
-            int64_t i = 0;
-            for (int64_t c = 0; c < n_chunks; ++c) {
-                mbar_wait_relaxed(empty + s, ph ^ 1u, 128);
-                const uint32_t bytes = (t == bc.slots - 1) ? bc.last_bytes : bc.chunk_bytes;
-                mbar_arrive_expect_tx(full + s, bytes);
-                bulk_g2s(ring + static_cast<size_t>(s) * bc.chunk_bytes,
-                         src + (blockIdx.x + i * gridDim.x) * img_bytes + static_cast<size_t>(t) * bc.chunk_bytes, bytes,
-                         full + s, pol);
-                if (++s == bc.ST) { s = 0; ph ^= 1u; }
-                if (++t == bc.slots) { t = 0; ++i; }
-            }
-        }
-        return;
-    }
-    if (warp <= bc.ND) {                                           // ---- decode warps
-        const int d = warp - 1;
-        // chunk c = d, d + ND, ...: image i = c / slots, slot t = c % slots, stage s = c % ST and its
-        // phase, NMS warp w = i % NN and its round - all kept incrementally
-        int64_t i = d / bc.slots;
-        int t = d % bc.slots, s = d % bc.ST, w = static_cast<int>(i % bc.NN);
-        uint32_t ph = static_cast<uint32_t>((d / bc.ST) & 1), r = static_cast<uint32_t>((i / bc.NN) & 1);
-        const int di = bc.ND / bc.slots, dt = bc.ND % bc.slots;        // step of (i, t) per chunk stride
-        for (int64_t c = d; c < n_chunks; c += bc.ND) {
-            const int cell = 32 * t + lane;
-            const bool valid = cell < cfg.M;
-            const int row = cell / cfg.S, col = cell - row * cfg.S;
-            int cls = 0;
-            float conf = -INFINITY;
-            float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-            mbar_wait(full + s, ph);
-            if (valid)
-                decode_cell<CT, BT>(reinterpret_cast<const float *>(ring + static_cast<size_t>(s) * bc.chunk_bytes) + lane * cfg.D,
-                                    cfg, static_cast<float>(col), static_cast<float>(row), cls, conf, box);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + s);                 // chunk is in registers: hand the stage back
-            mbar_wait(in_empty + w, r ^ 1u);                       // the NMS warp has taken its previous image
-            unsigned char *in = areas + static_cast<size_t>(w) * per_nms + cfg.ws_bytes;
-            if (valid) {
-                reinterpret_cast<float4 *>(in)[cell] = box;
-                reinterpret_cast<float *>(in + MP * 16)[cell] = conf;
-                reinterpret_cast<int *>(in + MP * 20)[cell] = cls;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(in_full + w);
-            // advance to chunk c + ND
-            s += bc.ND;                                            // ST is a multiple of ND: one wrap at most
-            if (s >= bc.ST) { s -= bc.ST; ph ^= 1u; }
-            int wi = di;
-            t += dt;
-            if (t >= bc.slots) { t -= bc.slots; ++wi; }
-            i += wi;
-            w += wi;
-            while (w >= bc.NN) { w -= bc.NN; r ^= 1u; }
-        }
-        return;
-    }
-    // ---- NMS warps
-    const int w = warp - 1 - bc.ND;
-    if (w >= bc.NN) return;
-    WarpWs<NS, false> ws(areas + static_cast<size_t>(w) * per_nms);
-    const unsigned char *in = areas + static_cast<size_t>(w) * per_nms + cfg.ws_bytes;
-    if (bc.pairs) ws.enable_pairs(areas + static_cast<size_t>(w) * per_nms + cfg.ws_bytes + bc.in_bytes);
-    for (int i = lane; i < cfg.tbl_rows * NS; i += 32) ws.tbl[i] = 0u;
-    __syncwarp();
-    bool valid[NS];
-#pragma unroll
-    for (int t = 0; t < NS; ++t) valid[t] = (lane + 32 * t) < cfg.M;
-    uint32_t r = 0;
-    for (int64_t i = w; i < my_imgs; i += bc.NN, r ^= 1u) {
-        float conf[NS];
-        float4 box[NS];
-        int cls[NS];
-        mbar_wait(in_full + w, r);
-#pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            conf[t] = -INFINITY; cls[t] = 0; box[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid[t]) {
-                const int cell = lane + 32 * t;
-                box[t] = reinterpret_cast<const float4 *>(in)[cell];
-                conf[t] = reinterpret_cast<const float *>(in + MP * 16)[cell];
-                cls[t] = reinterpret_cast<const int *>(in + MP * 20)[cell];
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(in_empty + w);
-        const int64_t img = blockIdx.x + i * gridDim.x;
-        const int K = nms_warp<NS, false>(conf, box, cls, valid, cfg, ws, out_boxes + img * cfg.M * 6,
-                                          out_idx ? out_idx + img * cfg.M : nullptr);
-        if (lane == 0) out_count[img] = K;
     }
 }
 
@@ -1414,7 +1019,7 @@ static int fill_cfg(NmsCfg &cfg, int S, int B, int C, float iou_thr, float conf_
     cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
     cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
     cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr;
-    cfg.ws_bytes = 0; cfg.tbl_rows = C; cfg.stage_bytes = 0; cfg.score_mode = 0;
+    cfg.ws_bytes = 0; cfg.tbl_rows = C; cfg.score_mode = 0;
     set_thr(cfg);
     return YH_OK;
 }
@@ -1424,21 +1029,9 @@ static int launch_direct(const float *pred, int64_t n, NmsCfg cfg, float *out_bo
                          cudaStream_t st)
 {
     cfg.ws_bytes = WarpWs<NS, false>::bytes(cfg.tbl_rows);
-    const int64_t img_bytes = 4ll * cfg.M * cfg.D;
-    const int last_cells = cfg.M - 32 * ((cfg.M - 1) / 32);
-    // Measured on B200 (S=14, B=3, C=80, 131072 images): cells read straight from global/L1 with
-    // ~24 resident warps per SM 5.9 ms; per-slot LDG staging (10 warps/SM) 7.6 ms; per-warp
-    // cp.async.bulk double buffer (6 warps/SM) 8.0 ms - the per-image work is a serial chain per warp,
-    // so resident warps matter more than load efficiency.  Default = no staging; the other two stay
-    // selectable (YH_DIRECT_STAGE=1, YH_WARP_TMA=1) for experiments.
-    const bool bulk_ok = env_int("YH_WARP_TMA", 0) != 0 && reinterpret_cast<uintptr_t>(pred) % 16 == 0 &&
-                         img_bytes % 16 == 0 && (static_cast<int64_t>(last_cells) * cfg.D * 4) % 16 == 0 &&
-                         img_bytes > 12 * 1024;
-    const bool stage = bulk_ok || env_int("YH_DIRECT_STAGE", 0) != 0;
-    cfg.stage_bytes = stage ? ((32 * cfg.D * 4 + 15) & ~15) : 0;
-    const size_t per_warp = static_cast<size_t>(cfg.ws_bytes) + (bulk_ok ? 2 * cfg.stage_bytes + 16 : cfg.stage_bytes);
+    const size_t per_warp = static_cast<size_t>(cfg.ws_bytes);
     if (per_warp > 220 * 1024) {
-        set_error("decode_nms: per-warp workspace %zu B does not fit shared memory (C + 5B = %d too large)", per_warp, cfg.D);
+        set_error("decode_nms: per-warp workspace %zu B does not fit shared memory (C = %d too large)", per_warp, cfg.C);
         return YH_ERR_UNSUPPORTED;
     }
     // as many warps as fit one SM, in two blocks when there are enough of them
@@ -1446,7 +1039,7 @@ static int launch_direct(const float *pred, int64_t n, NmsCfg cfg, float *out_bo
     int wpb = warps_sm >= 8 ? std::min(16, warps_sm / 2) : warps_sm;
     if (wpb < 1) wpb = 1;
     const size_t smem = static_cast<size_t>(wpb) * per_warp;
-    auto kern = bulk_ok ? decode_nms_warp_tma_kernel<NS, CT, BT> : decode_nms_direct_kernel<NS, CT, BT>;
+    auto kern = decode_nms_direct_kernel<NS, CT, BT>;
     YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 1;
     YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
@@ -1454,7 +1047,7 @@ static int launch_direct(const float *pred, int64_t n, NmsCfg cfg, float *out_bo
     const int64_t want = (n + wpb - 1) / wpb;
     const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * per_sm));
     kern<<<grid, wpb * 32, smem, st>>>(pred, n, cfg, out_boxes, out_count, out_idx);
-    YH_LAUNCH_CHECK(bulk_ok ? "decode_nms_warp_tma_kernel" : "decode_nms_direct_kernel");
+    YH_LAUNCH_CHECK("decode_nms_direct_kernel");
     return YH_OK;
 }
 
@@ -1491,48 +1084,6 @@ static int launch_coop(const float *pred, int64_t n, NmsCfg cfg, float *out_boxe
     const int grid = static_cast<int>(std::min<int64_t>(n, sm_count()));
     kern<<<grid, 32 * (1 + cc.NTEAM * cc.TW), smem, st>>>(pred, cfg, cc, out_boxes, out_count, out_idx);
     YH_LAUNCH_CHECK("decode_nms_coop_kernel");
-    *launched = true;
-    return YH_OK;
-}
-
-// Big images: chunked TMA ring + decode warps + NMS warps (decode_nms_big_kernel).  Returns
-// YH_OK with *launched = false when the shape does not qualify (the caller falls back to the direct kernel).
-template <int NS, int CT, int BT>
-static int launch_big(const float *pred, int64_t n, NmsCfg cfg, float *out_boxes, int *out_count, int *out_idx,
-                      cudaStream_t st, bool *launched)
-{
-    *launched = false;
-    const int64_t img_bytes = 4ll * cfg.M * cfg.D;
-    if (env_int("YH_BIG", 1) == 0 || reinterpret_cast<uintptr_t>(pred) % 16 != 0 || img_bytes % 16 != 0) return YH_OK;
-    BigCfg bc;
-    bc.slots = (cfg.M + 31) / 32;
-    bc.chunk_bytes = 32u * cfg.D * 4u;
-    bc.last_bytes = static_cast<uint32_t>(img_bytes - static_cast<int64_t>(bc.slots - 1) * bc.chunk_bytes);
-    bc.in_bytes = 32 * NS * 24;
-    bc.n = n;
-    cfg.ws_bytes = WarpWs<NS, false>::bytes(cfg.tbl_rows);
-    bc.pairs = (NS > 2 && env_int("YH_BIG_PAIRS", 1) != 0) ? 1 : 0;
-    bc.pair_bytes = bc.pairs ? ((WarpWs<NS, false>::pair_bytes() + 15) & ~15) : 0;
-    const size_t per_nms = static_cast<size_t>(cfg.ws_bytes) + bc.in_bytes + bc.pair_bytes;
-    // at most 16 warps at 128 registers: 1 producer + ND decode + NN NMS.  The ring holds K stages per
-    // decode warp (ST = K * ND, see the kernel comment); ND <= chunks per image.
-    bc.ND = std::max(1, std::min(std::min(8, bc.slots), env_int("YH_BIG_ND", 3)));
-    bc.NN = std::max(1, std::min(15 - bc.ND, env_int("YH_BIG_NN", bc.pairs ? 8 : 10)));
-    int K = std::max(1, std::min(4, env_int("YH_BIG_K", 2)));
-    auto need = [&](int nn, int stg) {
-        return static_cast<size_t>(stg) * bc.chunk_bytes + (2 * static_cast<size_t>(stg) + 2 * nn) * 8 + 16 + nn * per_nms + 128;
-    };
-    while (K > 1 && need(bc.NN, K * bc.ND) > 227 * 1024) --K;
-    while (bc.NN > 2 && need(bc.NN, K * bc.ND) > 227 * 1024) --bc.NN;
-    while (bc.ND > 1 && need(bc.NN, K * bc.ND) > 227 * 1024) --bc.ND;
-    bc.ST = K * bc.ND;
-    if (need(bc.NN, bc.ST) > 227 * 1024 || bc.chunk_bytes % 16 != 0 || bc.last_bytes % 16 != 0) return YH_OK;
-    const size_t smem = need(bc.NN, bc.ST);
-    auto kern = decode_nms_big_kernel<NS, CT, BT>;
-    YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const int grid = static_cast<int>(std::min<int64_t>(n, sm_count()));
-    kern<<<grid, 32 * (1 + bc.ND + bc.NN), smem, st>>>(pred, cfg, bc, out_boxes, out_count, out_idx);
-    YH_LAUNCH_CHECK("decode_nms_big_kernel");
     *launched = true;
     return YH_OK;
 }
@@ -1582,13 +1133,10 @@ static int launch_fused(const float *pred, int64_t n, NmsCfg cfg, float *out_box
             }
         }
     }
-    // ---- images too large for the tile ring: chunked ring + warp specialisation ----
+    // ---- images too large for the tile ring: cooperative team kernel ----
     if (done == 0 && img_bytes > 12 * 1024) {
         bool launched = false;
-        int rc = launch_coop<CT, BT>(pred, n, cfg, out_boxes, out_count, out_idx, st, &launched);
-        if (rc != YH_OK) return rc;
-        if (launched) return YH_OK;
-        rc = launch_big<NS, CT, BT>(pred, n, cfg, out_boxes, out_count, out_idx, st, &launched);
+        const int rc = launch_coop<CT, BT>(pred, n, cfg, out_boxes, out_count, out_idx, st, &launched);
         if (rc != YH_OK) return rc;
         if (launched) return YH_OK;
     }
@@ -1680,7 +1228,7 @@ extern "C" int yh_nms(const float *boxes, int64_t n, int M, float iou_thr, float
                "nms: boxes and out_boxes must be 8-byte aligned");
     NmsCfg cfg;
     cfg.S = 0; cfg.B = 0; cfg.C = 0; cfg.M = M; cfg.D = 6; cfg.inv_s = 0.f;
-    cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.stage_bytes = 0; cfg.score_mode = 0;
+    cfg.iou_thr = iou_thr; cfg.conf_thr = conf_thr; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.score_mode = 0;
     set_thr(cfg);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (pick_ns(M)) {
@@ -1699,7 +1247,7 @@ extern "C" int yh_decode(const float *pred, int64_t n, int S, int B, int C, floa
     YH_REQUIRE(S >= 1 && B >= 1 && C >= 1 && n >= 0, "decode: bad sizes");
     cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
     cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
-    cfg.iou_thr = cfg.conf_thr = 0.f; cfg.ws_bytes = 0; cfg.tbl_rows = 0; cfg.stage_bytes = 0;
+    cfg.iou_thr = cfg.conf_thr = 0.f; cfg.ws_bytes = 0; cfg.tbl_rows = 0;
     cfg.thr_fast = 0; cfg.score_mode = 0;
     if (n == 0) return YH_OK;
     YH_REQUIRE(pred && out_boxes, "decode: null pointer");

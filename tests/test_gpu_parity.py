@@ -107,20 +107,14 @@ def test_decode_nms_paths_agree(dev, monkeypatch):
     flat = _cuda(np.concatenate([np.zeros(2, F32), p.ravel()]), dev)[2:].reshape(p.shape)
     assert flat.data_ptr() % 16 == 8
     _check_nms(yu.decode_nms(flat, 20, 2, return_index=True), want, "8B-aligned")
-    for var in ("YH_DIRECT_STAGE", "YH_WARP_TMA"):           # the two staged variants of the direct kernel
-        monkeypatch.setenv("YH_TMA", "0"); monkeypatch.setenv(var, "1")
-        _check_nms(yu.decode_nms(_cuda(p, dev), 20, 2, return_index=True), want, var)
-        ps = F.synth_stress(8)
-        _check_nms(yu.decode_nms(_cuda(ps, dev), 80, 3, 0.5, 0.05, return_index=True), cport.decode_nms(ps, 80, 3, 0.5, 0.05), var + " stress")
-        monkeypatch.delenv("YH_TMA"); monkeypatch.delenv(var)
-    # big images: cooperative team kernel (default, several team / ring geometries), the warp-specialised
-    # kernel behind it (YH_COOP=0, with and without the pair-parallel IoU phase), the direct kernel (YH_BIG=0)
+    # big images: cooperative team kernel (default, several team / ring geometries) and the direct kernel
+    # behind it (YH_COOP=0); the exact-division variant of the IoU test
     ps = F.synth_stress(40)
     pq = F.synth_quantised(24, 14, 3, 80, seed=9)
     want_s, want_q = cport.decode_nms(ps, 80, 3, 0.5, 0.05), cport.decode_nms(pq, 80, 3, 0.5, 0.05)
     for env in ({}, {"YH_COOP_TEAMS": "1"}, {"YH_COOP_TEAMS": "2", "YH_COOP_STAGES": "3"}, {"YH_COOP_STAGES": "16"},
-                {"YH_COOP": "0"}, {"YH_COOP": "0", "YH_BIG_PAIRS": "0"}, {"YH_COOP": "0", "YH_BIG_ND": "2", "YH_BIG_NN": "5"},
-                {"YH_COOP": "0", "YH_BIG": "0"}, {"YH_EXACT_DIV": "1"}):
+                {"YH_COOP_TEAMS": "3", "YH_COOP_STAGES": "7"}, {"YH_COOP": "0"}, {"YH_EXACT_DIV": "1"},
+                {"YH_COOP": "0", "YH_EXACT_DIV": "1"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         _check_nms(yu.decode_nms(_cuda(ps, dev), 80, 3, 0.5, 0.05, return_index=True), want_s, f"stress {env}")
