@@ -530,7 +530,7 @@ struct TmaCfg {
 };
 
 template <int NS, int CT, int BT>
-__global__ void __launch_bounds__(800, 1) decode_nms_tma_kernel(const float *__restrict__ pred, NmsCfg cfg, TmaCfg tc,
+__global__ void __launch_bounds__(864, 1) decode_nms_tma_kernel(const float *__restrict__ pred, NmsCfg cfg, TmaCfg tc,
                                                                 float *__restrict__ out_boxes,
                                                                 int *__restrict__ out_count, int *__restrict__ out_idx)
 {
@@ -1099,8 +1099,8 @@ static int launch_fused(const float *pred, int64_t n, NmsCfg cfg, float *out_box
     if (tma_on && (reinterpret_cast<uintptr_t>(pred) % 16 == 0) && img_bytes <= 12 * 1024) {
         TmaCfg tc;
         tc.W = env_int("YH_TMA_W", 24);
-        tc.T = env_int("YH_TMA_T", 8);
-        if (tc.W < 1 || tc.W > 24) tc.W = 24;
+        tc.T = env_int("YH_TMA_T", 4);
+        if (tc.W < 1 || tc.W > 26) tc.W = 24;
         if (tc.T < 1) tc.T = 8;
         while (tc.T > 1 && ((tc.W % tc.T) != 0 || tc.T * img_bytes > 64 * 1024)) tc.T >>= 1;
         if ((tc.W % tc.T) == 0 && (tc.T * img_bytes) % 16 == 0 && n >= tc.T) {
@@ -1110,14 +1110,14 @@ static int launch_fused(const float *pred, int64_t n, NmsCfg cfg, float *out_box
             // a stage's mbarrier are strictly sequential (parity waits are only unambiguous one
             // phase apart): the stage count is a multiple of the group count G = W / T.
             int G = tc.W / tc.T;
-            size_t fixed = 2 * 8 * 8 /*barriers*/ + 16 + static_cast<size_t>(tc.W) * cfg.ws_bytes + 128;
-            int cap = std::min(8, env_int("YH_TMA_STAGES", 8));
+            size_t fixed = 2 * 16 * 8 /*barriers*/ + 16 + static_cast<size_t>(tc.W) * cfg.ws_bytes + 128;
+            int cap = std::min(16, env_int("YH_TMA_STAGES", 16));
             auto fit = [&](size_t fx) { return fx >= 227 * 1024 ? 0 : static_cast<int>((227 * 1024 - fx) / tc.tile_bytes); };
             int stages = (std::min(cap, fit(fixed)) / G) * G;
             if (stages < G || stages < 2) {             // not enough room: one group only
                 tc.W = tc.T;
                 G = 1;
-                fixed = 2 * 8 * 8 + 16 + static_cast<size_t>(tc.W) * cfg.ws_bytes + 128;
+                fixed = 2 * 16 * 8 + 16 + static_cast<size_t>(tc.W) * cfg.ws_bytes + 128;
                 stages = std::min(cap, fit(fixed));
             }
             tc.ST = stages;
