@@ -372,6 +372,41 @@ def other_configs(torch, dev, L, _lib, yu, sp):
             ts.append(a.elapsed_time(b))
         return statistics.mean(ts), min(ts)
 
+    # cfg1: batch 64 (BASELINE configs[0], the reference's own CPU-runnable case): launch-bound, so also as a CUDA graph
+    p64 = torch.from_numpy(F.synth_dense(64, seed=1234)).to(dev)
+    b64 = torch.empty((64, M, 6), device=dev); c64 = torch.empty((64,), device=dev, dtype=torch.int32)
+    f64 = lambda spx=sp: _lib.check(L.yh_decode_nms(p64.data_ptr(), 64, S, B, C, IOU_THR, CONF_THR, b64.data_ptr(), c64.data_ptr(), None, spx))
+
+    def per_call_us(fn, reps=300):
+        for _ in range(20):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return 1e3 * a.elapsed_time(b) / reps
+    plain_us = per_call_us(f64)
+    gs = torch.cuda.Stream(device=dev)
+    gs.wait_stream(torch.cuda.current_stream(dev))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(gs):
+        f64(ctypes.c_void_p(gs.cuda_stream))
+        gs.synchronize()
+        with torch.cuda.graph(graph, stream=gs):
+            f64(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    torch.cuda.current_stream(dev).wait_stream(gs)
+    graph_us = per_call_us(graph.replay)
+    from oracle import cport as _cp
+    x64 = p64.cpu().numpy()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        _, c_cpu, _ = _cp.decode_nms(x64, C, B, IOU_THR, CONF_THR, nthreads=1, want_idx=False)
+    cpu_us = (time.perf_counter() - t0) / 50 * 1e6
+    out["cfg1_batch64"] = {"us_per_call_back_to_back": plain_us, "us_per_cuda_graph_replay": graph_us,
+                           "cpu_port_1_thread_us": cpu_us, "counts_equal_cpu": bool(np.array_equal(c_cpu, c64.cpu().numpy()))}
     # cfg2 sparse: confidences u^32, ~2.7 candidates per image
     n = env_int("YH_BENCH_IMAGES", 1_000_000)
     gen = torch.Generator(device=dev); gen.manual_seed(2025)
