@@ -943,23 +943,58 @@ __global__ void __launch_bounds__(256) nms_rows_kernel(const float *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// decode only (utils.py:152-218): one thread per cell, rows written as 3 x float2.
+// decode only (utils.py:152-218).  A block takes 256 consecutive cells: their 256 * D input floats
+// are one contiguous chunk, staged in shared memory with coalesced 128-bit loads; thread = cell
+// decodes from shared memory; the 256 rows (6 floats each, again one contiguous chunk) go back
+// through shared memory as coalesced 128-bit stores.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) decode_kernel(const float *__restrict__ pred, int64_t n_cells, NmsCfg cfg,
-                                                     float *__restrict__ out)
+constexpr int kDecodeCells = 256;
+
+template <int CT, int BT>
+__global__ void __launch_bounds__(kDecodeCells) decode_kernel(const float *__restrict__ pred, int64_t n_cells, NmsCfg cfg,
+                                                              float *__restrict__ out)
 {
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_cells;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int cell = static_cast<int>(i % cfg.M);
-        int cls;
-        float conf;
-        float4 box;
-        decode_cell<0, 0>(pred + i * cfg.D, cfg, static_cast<float>(cell % cfg.S), static_cast<float>(cell / cfg.S), cls,
-                          conf, box);
-        float2 *o = reinterpret_cast<float2 *>(out + i * 6);
-        o[0] = make_float2(static_cast<float>(cls), conf);
-        o[1] = make_float2(box.x, box.y);
-        o[2] = make_float2(box.z, box.w);
+    extern __shared__ float4 dsm4[];
+    float *sin = reinterpret_cast<float *>(dsm4);                       // [256][D]
+    float *sout = sin + kDecodeCells * cfg.D;                           // [256][6]
+    const int64_t n_blk = (n_cells + kDecodeCells - 1) / kDecodeCells;
+    for (int64_t blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+        const int64_t c0 = blk * kDecodeCells;
+        const int cells = static_cast<int>(min(static_cast<int64_t>(kDecodeCells), n_cells - c0));
+        const float *src = pred + c0 * cfg.D;
+        const int nfl = cells * cfg.D;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            for (int i = threadIdx.x; i < (nfl >> 2); i += kDecodeCells) dsm4[i] = __ldcs(s4 + i);
+            for (int i = (nfl & ~3) + threadIdx.x; i < nfl; i += kDecodeCells) sin[i] = src[i];
+        } else {
+            for (int i = threadIdx.x; i < nfl; i += kDecodeCells) sin[i] = src[i];
+        }
+        __syncthreads();
+        if (static_cast<int>(threadIdx.x) < cells) {
+            const int cell = static_cast<int>((c0 + threadIdx.x) % cfg.M);
+            int cls;
+            float conf;
+            float4 box;
+            decode_cell<CT, BT>(sin + threadIdx.x * cfg.D, cfg, static_cast<float>(cell % cfg.S), static_cast<float>(cell / cfg.S),
+                                cls, conf, box);
+            float2 *o = reinterpret_cast<float2 *>(sout + threadIdx.x * 6);
+            o[0] = make_float2(static_cast<float>(cls), conf);                    // utils.py:175, 213
+            o[1] = make_float2(box.x, box.y);
+            o[2] = make_float2(box.z, box.w);
+        }
+        __syncthreads();
+        float *dst = out + c0 * 6;
+        const int nout = cells * 6;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const float4 *so4 = reinterpret_cast<const float4 *>(sout);
+            float4 *d4 = reinterpret_cast<float4 *>(dst);
+            for (int i = threadIdx.x; i < (nout >> 2); i += kDecodeCells) __stcs(d4 + i, so4[i]);
+            for (int i = (nout & ~3) + threadIdx.x; i < nout; i += kDecodeCells) dst[i] = sout[i];
+        } else {
+            for (int i = threadIdx.x; i < nout; i += kDecodeCells) dst[i] = sout[i];
+        }
+        __syncthreads();                                                          // shared memory is reused
     }
 }
 
@@ -1253,8 +1288,20 @@ extern "C" int yh_decode(const float *pred, int64_t n, int S, int B, int C, floa
     YH_REQUIRE(pred && out_boxes, "decode: null pointer");
     YH_REQUIRE(reinterpret_cast<uintptr_t>(out_boxes) % 8 == 0, "decode: out_boxes must be 8-byte aligned");
     const int64_t cells = n * cfg.M;
-    const int grid = static_cast<int>(std::min<int64_t>((cells + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
-    decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred, cells, cfg, out_boxes);
+    size_t smem = static_cast<size_t>(kDecodeCells) * (cfg.D + 6) * 4;
+    smem = (smem + 15) & ~static_cast<size_t>(15);
+    if (smem > 227 * 1024) {
+        set_error("decode: C + 5B = %d too large for the shared-memory tile", cfg.D);
+        return YH_ERR_UNSUPPORTED;
+    }
+    const bool voc = (C == 20 && B == 2);
+    auto kern = voc ? decode_kernel<20, 2> : decode_kernel<0, 0>;
+    YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 1;
+    YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecodeCells, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int grid = static_cast<int>(std::min<int64_t>((cells + kDecodeCells - 1) / kDecodeCells, static_cast<int64_t>(sm_count()) * per_sm));
+    kern<<<grid, kDecodeCells, smem, static_cast<cudaStream_t>(stream)>>>(pred, cells, cfg, out_boxes);
     YH_LAUNCH_CHECK("decode_kernel");
     return YH_OK;
 }
