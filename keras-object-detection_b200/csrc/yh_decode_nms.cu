@@ -210,11 +210,28 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
 #pragma unroll
     for (int t = 0; t < NS; ++t) key[t] = kFloatCls ? ci[t] : cls[t];
     if (kFloatCls) {
-        for (int j = n - 1; j >= 0; --j) {
-            const float f = ws.cclsf[j];
+        // Row input carries the class as a float (utils.py:175).  Usual case: every candidate's class is a
+        // small non-negative integer -> the integer is the key, as in the fused kernels.  Otherwise (any
+        // float, NaN never equal to anything) fall back to "first candidate holding an equal class".
+        bool small_int = true;
 #pragma unroll
-            for (int t = 0; t < NS; ++t)
-                if (((pass_m >> t) & 1u) && f == __int_as_float(cls[t])) key[t] = j;
+        for (int t = 0; t < NS; ++t) {
+            if ((pass_m >> t) & 1u) {
+                const float f = __int_as_float(cls[t]);
+                const int v = __float2int_rz(f);
+                small_int = small_int && (f == static_cast<float>(v)) && v >= 0 && v < cfg.tbl_rows;
+            }
+        }
+        if (__all_sync(FULL, small_int)) {
+#pragma unroll
+            for (int t = 0; t < NS; ++t) key[t] = __float2int_rz(__int_as_float(cls[t]));
+        } else {
+            for (int j = n - 1; j >= 0; --j) {
+                const float f = ws.cclsf[j];
+#pragma unroll
+                for (int t = 0; t < NS; ++t)
+                    if (((pass_m >> t) & 1u) && f == __int_as_float(cls[t])) key[t] = j;
+            }
         }
     }
     __syncwarp();   // every lane is done with smeta (scratch) and ckey before they are rewritten

@@ -181,6 +181,16 @@ def test_nms_rows_entry(dev):
         outs = yu.non_max_suppression(_cuda(rows, dev), 0.4, 0.3)
         for i in range(6):
             assert np.array_equal(outs[i].cpu().numpy(), O.non_max_suppression(rows[i], 0.4, 0.3)), (M, i)
+    # integral classes take the integer-key path; -0.0 == +0.0; a class beyond the table (1000.) falls back
+    for M in (49, 196):
+        rows = rng.random((5, M, 6), dtype=F32)
+        rows[..., 0] = rng.integers(0, 3, (5, M)).astype(F32)
+        rows[1, ::3, 0] = -0.0
+        rows[2, ::4, 0] = 1000.0
+        rows[..., 4:6] = 0.2 + 0.4 * rows[..., 4:6]
+        outs = yu.non_max_suppression(_cuda(rows, dev), 0.4, 0.3)
+        for i in range(5):
+            assert np.array_equal(outs[i].cpu().numpy(), O.non_max_suppression(rows[i], 0.4, 0.3)), (M, i)
     assert yu.non_max_suppression(_cuda(rows[0], dev), 0.5, 2.0).shape == (0, 6)
     assert yu.non_max_suppression_2(_cuda(rows[0], dev)).shape[1] == 6
 
