@@ -172,9 +172,17 @@ YH_API int yh_encode_labels(const double *boxes, const int64_t *offsets, int64_t
 /* N3 - head adapter (train.py:208, model.py:107).  A flat (N, S*S*(C+5B)) head output IS the
  * (N,S,S,C+5B) tensor - pass the same pointer to the entry points above.  A half-precision head
  * is widened exactly to float32 first: src_dtype YH_DTYPE_F16 / YH_DTYPE_BF16, n elements. */
+#define YH_DTYPE_F32 0
 #define YH_DTYPE_F16 1
 #define YH_DTYPE_BF16 2
 YH_API int yh_head_to_f32(const void *src, int src_dtype, int64_t n, float *dst, void *stream);
+
+/* The same adapter fused into the hot path: yh_decode_nms_ex on a prediction tensor of element type
+ * `dtype` (YH_DTYPE_F32 / _F16 / _BF16).  A half-precision head is widened exactly as it is read, so the
+ * results equal yh_decode_nms_ex on the widened tensor while the kernel reads half the bytes. */
+YH_API int yh_decode_nms_typed(const void *pred, int dtype, int64_t n, int S, int B, int C,
+                        float iou_thr, float conf_thr, int score_mode,
+                        float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, void *stream);
 
 /* N4 - utils.py:652-655 (get_tagged_img / get_grid_tagged_img): pixel corners of kept rows,
  * xmin = int((cx - w/2) * width), ... in float32, int() truncating toward zero.

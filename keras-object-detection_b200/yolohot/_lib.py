@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("YH_LIB_PATH") or os.path.join(_HERE, "libyolohot.so")   # YH_LIB_PATH: A/B builds
 
 YH_OK, YH_ERR_ARG, YH_ERR_CUDA, YH_ERR_NCCL, YH_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-YH_DTYPE_F16, YH_DTYPE_BF16 = 1, 2
+YH_DTYPE_F32, YH_DTYPE_F16, YH_DTYPE_BF16 = 0, 1, 2
 
 _lib = None
 
@@ -20,7 +20,7 @@ SYMBOLS = (
     "yh_version", "yh_last_error", "yh_device_info", "yh_launch_count",
     "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_ex", "yh_decode_nms_host", "yh_rows_append",
     "yh_loss", "yh_map_match", "yh_map_reduce",
-    "yh_encode_labels", "yh_head_to_f32", "yh_pixel_boxes",
+    "yh_encode_labels", "yh_head_to_f32", "yh_decode_nms_typed", "yh_pixel_boxes",
     "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_workspace_bytes",
     "yh_iou_dl", "yh_decode_dl", "yh_nms_dl", "yh_decode_nms_dl", "yh_loss_dl",
 )
@@ -57,6 +57,7 @@ def lib():
     L.yh_map_reduce.argtypes = [vp, vp, i64, vp, i, vp, vp, vp]
     L.yh_encode_labels.argtypes = [vp, vp, i64, i, i, i, vp, vp, vp]
     L.yh_head_to_f32.argtypes = [vp, i, i64, vp, vp]
+    L.yh_decode_nms_typed.argtypes = [vp, i, i64, i, i, i, f, f, i, vp, vp, vp, vp]
     L.yh_pixel_boxes.argtypes = [vp, vp, i64, i, i, i, vp, vp]
     L.yh_comm_init_all.argtypes = [i, vp, vp]
     L.yh_comm_destroy.argtypes = [vp]

@@ -158,7 +158,13 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
                                         kidx.ctypes.data if return_index else None, torch.cuda.current_device()),
                    "decode_nms")
         return (boxes, cnt, kidx) if return_index else (boxes, cnt)
-    p, kind = as_device_f32(predictions)
+    half = isinstance(predictions, torch.Tensor) and predictions.is_cuda and predictions.dtype in (torch.float16, torch.bfloat16)
+    if half:                        # half-precision head: widened inside the kernel (yh_decode_nms_typed), half the HBM bytes
+        p, kind = predictions.contiguous(), "torch"
+        if p.data_ptr() % 4:        # the kernels read element pairs: a 2-byte aligned view is re-based
+            p = p.clone()
+    else:
+        p, kind = as_device_f32(predictions)
     p, n, S = as_grid(p, num_classes, num_boxes, grid)
     if out is not None:
         boxes, cnt = out[0], out[1]
@@ -168,7 +174,13 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
         cnt = torch.empty((n,), dtype=torch.int32, device=p.device)
         kidx = torch.empty((n, S * S), dtype=torch.int32, device=p.device) if return_index else None
     with torch.cuda.device(p.device):
-        if score_mode == "conf":
+        if half:
+            code = _lib.YH_DTYPE_F16 if p.dtype == torch.float16 else _lib.YH_DTYPE_BF16
+            _lib.check(L.yh_decode_nms_typed(p.data_ptr(), code, n, S, int(num_boxes), int(num_classes), float(iou_threshold),
+                                             float(conf_threshold), 0 if score_mode == "conf" else 1, boxes.data_ptr(),
+                                             cnt.data_ptr(), kidx.data_ptr() if kidx is not None else None,
+                                             stream_ptr(p.device)), "decode_nms")
+        elif score_mode == "conf":
             hp, hb, hc, hk = DL(p), DL(boxes), DL(cnt), dl(kidx)
             _lib.check(L.yh_decode_nms_dl(hp.ptr, int(num_boxes), int(num_classes), float(iou_threshold),
                                           float(conf_threshold), hb.ptr, hc.ptr, ptr(hk), stream_ptr(p.device)), "decode_nms")

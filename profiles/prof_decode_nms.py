@@ -47,3 +47,18 @@ ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
 kept = int(cnt.sum())
 print(f"{mode}: n={n} S={S} B={B} C={C} ms={['%.3f' % m for m in ms]} kept/img={kept / n:.2f} "
       f"GB/s(best)={(n * (4 * S * S * D + 4) + 24 * kept) / min(ms) / 1e6:.0f}")
+
+# half-precision heads (YH_PROF_HALF=1): the same workload as bfloat16 / float16 through yh_decode_nms_typed
+if os.environ.get("YH_PROF_HALF"):
+    for dt, code in ((torch.bfloat16, _lib.YH_DTYPE_BF16), (torch.float16, _lib.YH_DTYPE_F16)):
+        ph = p.to(dt)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            _lib.check(L.yh_decode_nms_typed(ph.data_ptr(), code, n, S, B, C, 0.5, thr, 0, boxes.data_ptr(), cnt.data_ptr(), None, st))
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
+        kept = int(cnt.sum())
+        print(f"{mode} {dt}: ms={['%.3f' % m for m in ms]} kept/img={kept / n:.2f} "
+              f"GB/s(best)={(n * (2 * S * S * D + 4) + 24 * kept) / min(ms) / 1e6:.0f} images/s(best)={n / min(ms) / 1e3:.1f} M")

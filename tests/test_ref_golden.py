@@ -228,13 +228,34 @@ def test_cuda_head_adapter(dev):
     assert np.array_equal(yu.decode_predictions(flat, 20, 2).cpu().numpy(), R["dense_decode"])
     with pytest.raises(ValueError):
         yu.decode_nms(flat[:, :-1].contiguous(), 20, 2)
+    from yolohot._tensor import head_to_f32
     for dt in (torch.float16, torch.bfloat16):
         h = _cuda(p, dev).to(dt)
-        want = yu.decode_nms(h.float(), 20, 2)
-        got = yu.decode_nms(h, 20, 2)
+        assert torch.equal(head_to_f32(h), h.float())                      # the standalone adapter kernel is exact
+        want = yu.decode_nms(h.float(), 20, 2, return_index=True)
+        got = yu.decode_nms(h, 20, 2, return_index=True)                   # fused: widened inside the kernel
         assert torch.equal(got[1], want[1])
         m = torch.arange(49, device=dev)[None, :] < want[1][:, None]
-        assert torch.equal(got[0][m], want[0][m])
+        assert torch.equal(got[0][m], want[0][m]) and torch.equal(got[2][m], want[2][m])
+        assert torch.equal(yu.decode_predictions(h, 20, 2), yu.decode_predictions(h.float(), 20, 2))
+    # half-precision heads through every fused kernel: tile ring + direct tail (VOC, odd count), cooperative
+    # team kernel (S=14, B=3, C=80), generic shapes, unaligned view, score-mode extension
+    from tests import fixtures as F
+    for (gen, n, S, B, C, it, ct) in ((F.synth_dense, 1003, 7, 2, 20, 0.5, 0.4), (F.synth_stress, 37, 14, 3, 80, 0.5, 0.05),
+                                      (F.synth_quantised, 50, 9, 2, 6, 0.5, 0.3), (F.synth_dense, 21, 13, 5, 7, 0.4, 0.3)):
+        x = _cuda(gen(n, S, B, C), dev)
+        for dt in (torch.float16, torch.bfloat16):
+            h = x.to(dt)
+            for mode in ("conf", "conf_x_prob"):
+                want = yu.decode_nms(h.float(), C, B, it, ct, return_index=True, score_mode=mode)
+                got = yu.decode_nms(h, C, B, it, ct, return_index=True, score_mode=mode)
+                assert torch.equal(got[1], want[1]), (S, dt, mode)
+                m = torch.arange(S * S, device=dev)[None, :] < want[1][:, None]
+                assert torch.equal(got[0][m], want[0][m]) and torch.equal(got[2][m], want[2][m]), (S, dt, mode)
+            odd = torch.cat([torch.zeros(1, dtype=dt, device=dev), h.reshape(-1)])[1:].reshape(h.shape)   # 2-byte aligned base
+            got = yu.decode_nms(odd, C, B, it, ct)
+            want = yu.decode_nms(h.float(), C, B, it, ct)
+            assert torch.equal(got[1], want[1])
     yt = _cuda(R["loss16_yt"], dev)
     yp = _cuda(R["loss16_yp"].reshape(16, -1), dev).requires_grad_(True)
     tot = yloss.YoloV1Loss(20, 2)(yt, yp)
