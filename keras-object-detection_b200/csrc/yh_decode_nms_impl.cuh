@@ -1057,7 +1057,11 @@ static int launch_fused(const E *pred, int64_t n, NmsCfg cfg, float *out_boxes, 
     int64_t done = 0;
     // ---- TMA ring for the aligned bulk ----
     const bool tma_on = env_int("YH_TMA", 1) != 0;
-    if (tma_on && (reinterpret_cast<uintptr_t>(pred) % 16 == 0) && img_bytes <= 12 * 1024) {
+    // Images above this size go to the cooperative team kernel instead of the tile ring: 12 KB in general (the ring would
+    // hold too few images), 6 KB for grids of more than 64 cells (NS > 2: long per-warp chains and register spills in the
+    // one-warp-per-image kernel; measured 2-3x in favour of the team kernel on S = 9..16, profiles/prof_midsize.py)
+    const int64_t coop_min = env_int("YH_COOP_MIN_BYTES", NS > 2 ? 6 * 1024 : 12 * 1024);
+    if (tma_on && (reinterpret_cast<uintptr_t>(pred) % 16 == 0) && img_bytes <= 12 * 1024 && img_bytes <= coop_min) {
         TmaCfg tc;
         tc.W = env_int("YH_TMA_W", 24);
         tc.T = env_int("YH_TMA_T", 4);
@@ -1095,7 +1099,7 @@ static int launch_fused(const E *pred, int64_t n, NmsCfg cfg, float *out_boxes, 
         }
     }
     // ---- images too large for the tile ring: cooperative team kernel ----
-    if (done == 0 && img_bytes > 12 * 1024) {
+    if (done == 0 && (img_bytes > 12 * 1024 || img_bytes > coop_min)) {
         bool launched = false;
         const int rc = launch_coop<CT, BT, E>(pred, n, cfg, out_boxes, out_count, out_idx, st, &launched);
         if (rc != YH_OK) return rc;
