@@ -68,6 +68,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.mem, self.power = [], []
         self._stop = threading.Event()
         self._t = None
         try:
@@ -84,13 +85,15 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.mem.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in {**self.BAD, **self.NOTE}.items():
                     if r & bit:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def __enter__(self):
         if self.nv is not None:
@@ -105,7 +108,10 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": (statistics.median(self.samples) if self.samples else None),
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "sm_mhz_min": (min(self.samples) if self.samples else None),
+                "mem_mhz": (statistics.median(self.mem) if self.mem else None),
+                "power_w_max": (max(self.power) if self.power else None)}
 
 
 # ------------------------------------------------------------------------------ reference arm
