@@ -272,10 +272,13 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
                 n_def = 0;
             }
             const int take = min(n_heavy - h0, cfg.defer_cap - n_def);
-            for (int e = threadIdx.x; e < take * 2 * D; e += blockDim.x) {
-                const int h = e / (2 * D), j = e - h * 2 * D;
+            for (int h = warp; h < take; h += nwarp) {                     // one warp per cell, lanes over its 2 D values
                 const int cell = heavy[h0 + h];
-                hdat[(n_def + h) * 2 * D + j] = (j < D) ? st[cell * D + j] : sp[cell * D + j - D];
+                float *dst = hdat + (n_def + h) * 2 * D;
+                for (int j = lane; j < D; j += 32) {
+                    dst[j] = st[cell * D + j];
+                    dst[D + j] = sp[cell * D + j];
+                }
             }
             for (int h = threadIdx.x; h < take; h += blockDim.x) hcell[n_def + h] = cell0 + heavy[h0 + h];
             n_def += take;
