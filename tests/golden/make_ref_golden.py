@@ -172,6 +172,19 @@ def main():
     yp = F.synth_map_pred(yt)
     g["map40_yt"], g["map40_yp"] = yt, yp
     g["map40_map"], g["map40_true_rows"], g["map40_pred_rows"] = evaluator([(yt[:25], yp[:25]), (yt[25:], yp[25:])], 20, 2)
+    # reset_states() only rewinds the image counter; the next update overwrites the buffers (utils.py:467-468, 484-486)
+    ev = RU.MeanAveragePrecision(20, 2)
+    ev.update_state(T(yt[:10]), T(yp[:10]))
+    ev.reset_states()
+    ev.update_state(T(yt[10:16]), T(yp[10:16]))
+    ev.update_state(T(yt[16:20]), T(yp[16:20]))
+    g["reset_map"] = np.float32(np.asarray(ev.result()))
+    g["reset_true_rows"], g["reset_pred_rows"] = np.asarray(ev.all_true_boxes_variable), np.asarray(ev.all_pred_boxes_variable)
+    # IoU on the 4-D shapes the loss feeds it (loss.py:128-131)
+    b1 = rng.random((3, 7, 7, 4), dtype=F32)
+    b2 = rng.random((3, 7, 7, 4), dtype=F32)
+    g["iou4d_a"], g["iou4d_b"] = b1, b2
+    g["iou4d_out"] = np.asarray(RU.intersection_over_union(T(b1), T(b2)))
     # direct call on hand-made rows: class without GT, class without detections, two detections
     # fighting for one GT, equal confidences (stable order), detection in an image without GT
     true_rows = np.array([[0, 0, 1, .5, .5, .2, .2], [0, 0, 1, .2, .2, .1, .1], [1, 0, 1, .5, .5, .2, .2],

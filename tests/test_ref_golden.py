@@ -79,6 +79,15 @@ def test_oracle_map_matches_reference_source():
     for key, thr in (("rows_map", 0.5), ("rows_map_thr03", 0.3)):
         got = O.mean_average_precision(R["rows_true"], R["rows_pred"], 4, thr)
         assert abs(float(got) - float(R[key])) <= 1e-6, (key, got, R[key])
+    ev = O.MeanAveragePrecision(20, 2)                                  # reset_states semantics (Q17)
+    ev.update_state(R["map40_yt"][:10], R["map40_yp"][:10])
+    ev.reset_states()
+    ev.update_state(R["map40_yt"][10:16], R["map40_yp"][10:16])
+    ev.update_state(R["map40_yt"][16:20], R["map40_yp"][16:20])
+    assert np.array_equal(ev.all_true_boxes_variable, R["reset_true_rows"])
+    assert np.array_equal(ev.all_pred_boxes_variable, R["reset_pred_rows"])
+    assert abs(float(ev.result()) - float(R["reset_map"])) <= 1e-6
+    assert np.array_equal(O.intersection_over_union(R["iou4d_a"], R["iou4d_b"]), R["iou4d_out"])
 
 
 def test_oracle_label_grids_match_reference_source():
@@ -183,6 +192,16 @@ def test_cuda_map_matches_reference_source(dev):
     for key, thr in (("rows_map", 0.5), ("rows_map_thr03", 0.3)):
         got = yu.mean_average_precision(_cuda(R["rows_true"], dev), _cuda(R["rows_pred"], dev), 4, thr)
         assert abs(float(got) - float(R[key])) <= 1e-6, (key, float(got), R[key])
+    ev = yu.MeanAveragePrecision(20, 2)                                 # reset_states semantics (Q17)
+    ev.update_state(_cuda(R["map40_yt"][:10], dev), _cuda(R["map40_yp"][:10], dev))
+    ev.reset_states()
+    ev.update_state(_cuda(R["map40_yt"][10:16], dev), _cuda(R["map40_yp"][10:16], dev))
+    ev.update_state(_cuda(R["map40_yt"][16:20], dev), _cuda(R["map40_yp"][16:20], dev))
+    assert np.array_equal(ev.all_true_boxes_variable.cpu().numpy(), R["reset_true_rows"])
+    assert np.array_equal(ev.all_pred_boxes_variable.cpu().numpy(), R["reset_pred_rows"])
+    assert abs(float(ev.result()) - float(R["reset_map"])) <= 1e-6
+    out = yu.intersection_over_union(_cuda(R["iou4d_a"], dev), _cuda(R["iou4d_b"], dev)).cpu().numpy()
+    assert out.shape == R["iou4d_out"].shape and np.array_equal(out, R["iou4d_out"])
 
 
 @pytest.mark.gpu
