@@ -333,10 +333,14 @@ def run_own(args):
                 break
         dt = time.perf_counter() - t0
         audit = bool(np.array_equal(c_cpu, cnt[:n_cpu].cpu().numpy()))
+        n1 = min(n_cpu, 32_768)                                     # the reference itself is single-threaded Python: 1-core figure too
+        t1 = time.perf_counter()
+        cport.decode_nms(sl[:n1], C, B, IOU_THR, CONF_THR, nthreads=1, want_idx=False)
+        one_core = n1 / (time.perf_counter() - t1)
         cpu_baseline = {"value": n_cpu * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"first {n_cpu} images of the same batch x {reps} passes ({dt:.1f} s), oracle C port "
                                   f"(reference itself is TF-eager Python, not importable: no TensorFlow)",
-                        "kept_counts_equal_gpu": audit}
+                        "kept_counts_equal_gpu": audit, "value_1_core": one_core}
         # ---- the other BASELINE configs, briefly (kernel time, resident inputs)
         extras = other_configs(torch, dev, L, _lib, yu, sp)
 
