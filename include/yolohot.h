@@ -96,6 +96,12 @@ YH_API int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int B, i
                        float *out_boxes_host, int32_t *out_count_host,
                        int32_t *out_keep_idx_host /* nullable */, int device);
 
+/* ---- confidence filter without NMS: metric.py:35-37, 81 (the stale evaluator's ground truth) ----
+ * rows (n, M, 6) -> out_rows (n, M, 6): the rows of image i with conf > conf_thr, cell order kept,
+ * packed at the front; out_count (n).  out_rows must not alias rows. */
+YH_API int yh_filter_rows(const float *rows, int64_t n, int M, float conf_thr,
+                   float *out_rows, int32_t *out_count, void *stream);
+
 /* ---- evaluator rows: utils.py:476-489 (prefix img_idx, append) ------------------------
  * Compacts padded NMS output (n, M, 6) + count (n) into rows [img, cls, conf, cx,cy,w,h]
  * appended at out_rows + 7 * (*row_cursor) ; image i gets img index img_base + i (as

@@ -174,9 +174,53 @@ __global__ void __launch_bounds__(256) pixel_boxes_kernel(const float *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Rows with conf > thr, cell order kept (the stale evaluator of metric.py:35-37, 81 thresholds the ground
+// truth but does not run NMS on it).  One warp per image, ballot/popc compaction slot by slot.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) filter_rows_kernel(const float *__restrict__ rows, int64_t n, int M, float conf_thr,
+                                                          float *__restrict__ out, int *__restrict__ count)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int64_t img = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); img < n;
+         img += static_cast<int64_t>(gridDim.x) * wpb) {
+        const float2 *src = reinterpret_cast<const float2 *>(rows + img * M * 6);
+        float2 *dst = reinterpret_cast<float2 *>(out + img * M * 6);
+        int base = 0;
+        for (int i0 = 0; i0 < M; i0 += 32) {
+            const int i = i0 + lane;
+            float2 a = make_float2(0.f, 0.f), b = a, c = a;
+            if (i < M) { a = src[3 * i]; b = src[3 * i + 1]; c = src[3 * i + 2]; }
+            const bool pass = i < M && a.y > conf_thr;
+            const unsigned bal = __ballot_sync(FULLM, pass);
+            if (pass) {
+                const int pos = base + __popc(bal & ((1u << lane) - 1u));
+                dst[3 * pos] = a; dst[3 * pos + 1] = b; dst[3 * pos + 2] = c;
+            }
+            base += __popc(bal);
+        }
+        if (lane == 0) count[img] = base;
+    }
+}
+
 }  // namespace yh
 
 using namespace yh;
+
+extern "C" int yh_filter_rows(const float *rows, int64_t n, int M, float conf_thr, float *out_rows, int32_t *out_count,
+                              void *stream)
+{
+    YH_REQUIRE(n >= 0 && M >= 1, "filter_rows: bad sizes");
+    if (n == 0) return YH_OK;
+    YH_REQUIRE(rows && out_rows && out_count, "filter_rows: null pointer");
+    YH_REQUIRE(rows != out_rows, "filter_rows: in-place filtering is not supported");
+    YH_REQUIRE(reinterpret_cast<uintptr_t>(rows) % 8 == 0 && reinterpret_cast<uintptr_t>(out_rows) % 8 == 0,
+               "filter_rows: rows and out_rows must be 8-byte aligned");
+    const int grid = static_cast<int>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(sm_count()) * 8));
+    filter_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, n, M, conf_thr, out_rows, out_count);
+    YH_LAUNCH_CHECK("filter_rows_kernel");
+    return YH_OK;
+}
 
 extern "C" int yh_encode_labels(const double *boxes, const int64_t *offsets, int64_t n, int S, int B, int C, float *out,
                                 int32_t *out_bad, void *stream)

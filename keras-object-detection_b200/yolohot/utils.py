@@ -355,12 +355,13 @@ class MeanAveragePrecisionNumpy(MeanAveragePrecision):
 
 
 def _filter_rows(boxes, conf_threshold):
-    """metric.py:81 (stale evaluator): rows with conf > thr, cell order kept.  Implemented as an
-    NMS whose IoU threshold can never fire (IoU <= 1 < 2) followed by restoring cell order."""
+    """metric.py:81 (stale evaluator): rows with conf > thr, cell order kept (yh_filter_rows)."""
     n, M = int(boxes.shape[0]), int(boxes.shape[1])
-    out, cnt, kidx = _nms_device(boxes, 2.0, conf_threshold, want_idx=True)
-    order = torch.argsort(torch.where(kidx >= 0, kidx, torch.full_like(kidx, M)), dim=1, stable=True)
-    out = torch.gather(out, 1, order.unsqueeze(-1).expand(-1, -1, 6)).contiguous()
+    out = torch.empty((n, M, 6), dtype=torch.float32, device=boxes.device)
+    cnt = torch.empty((n,), dtype=torch.int32, device=boxes.device)
+    with torch.cuda.device(boxes.device):
+        _lib.check(_lib.lib().yh_filter_rows(boxes.data_ptr(), n, M, float(conf_threshold), out.data_ptr(), cnt.data_ptr(),
+                                             stream_ptr(boxes.device)), "filter_rows")
     return out, cnt
 
 
