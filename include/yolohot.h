@@ -155,6 +155,18 @@ YH_API int yh_map_allgather(void *comm, const uint64_t *const *keys, const uint8
                      int32_t *const *gt_per_class, int C, uint64_t *const *out_keys, uint8_t *const *out_tp,
                      int64_t out_capacity, void *const *streams);
 
+/* The exchange step FUSED into stage 1 over peer-mapped memory (NVLink / NVSwitch), no collective call: device
+ * `dev_index` matches its shard like yh_map_match and its last kernel stores every record (key, TP flag) at
+ * [offset, offset + np) of the record buffers of ALL devices, and adds its per-class ground-truth counts into all
+ * devices' accumulators gt_sum_all[d] (C int32 each, zeroed by the caller).  offset = number of detections of the
+ * shards before this one (device order = image order).  Needs yh_comm_p2p(comm) == 1.  Surround the calls of all
+ * devices with yh_comm_barrier: zero the accumulators, barrier, match on every device, barrier, yh_map_reduce. */
+YH_API int yh_comm_p2p(void *comm);
+YH_API int yh_comm_barrier(void *comm, void *const *streams);
+YH_API int yh_map_match_p2p(void *comm, int dev_index, const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
+                     int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
+                     int32_t *const *gt_sum_all, void *stream);
+
 /* Device scratch (bytes) an operation allocates internally for n images / rows; informational. */
 #define YH_OP_DECODE_NMS 1
 #define YH_OP_DECODE_NMS_HOST 2

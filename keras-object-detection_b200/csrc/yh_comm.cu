@@ -73,32 +73,42 @@ static int load_nccl()
         }                                                                                      \
     } while (0)
 
-struct Comm {
-    int ndev = 0;
-    std::vector<int> devs;
-    std::vector<ncclComm_t> comms;
-};
-
 }  // namespace yh
 
 using namespace yh;
 
 extern "C" int yh_comm_init_all(int ndev, const int *devs, void **comm)
 {
-    YH_REQUIRE(ndev >= 1 && ndev <= 64 && comm != nullptr, "comm_init_all: bad arguments");
+    YH_REQUIRE(ndev >= 1 && ndev <= kMaxPeers && comm != nullptr, "comm_init_all: bad arguments (at most %d devices)", kMaxPeers);
     int rc = load_nccl();
     if (rc != YH_OK) return rc;
     Comm *c = new Comm;
     c->ndev = ndev;
-    c->devs.resize(ndev);
     for (int i = 0; i < ndev; ++i) c->devs[i] = devs ? devs[i] : i;
-    c->comms.resize(ndev);
-    ncclResult_t r = g_nccl.CommInitAll(c->comms.data(), ndev, c->devs.data());
+    ncclResult_t r = g_nccl.CommInitAll(reinterpret_cast<ncclComm_t *>(c->comms), ndev, c->devs);
     if (r != 0) {
         set_error("NCCL error %d (%s) at ncclCommInitAll", r, g_nccl.GetErrorString(r));
         delete c;
         return YH_ERR_NCCL;
     }
+    // peer access for the fused match + scatter kernel (yh_map_match_p2p) and one event per device for yh_comm_barrier
+    int prev = 0;
+    cudaGetDevice(&prev);
+    c->p2p = true;
+    for (int i = 0; i < ndev; ++i) {
+        cudaSetDevice(c->devs[i]);
+        cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
+        for (int j = 0; j < ndev; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, c->devs[i], c->devs[j]);
+            if (!can) { c->p2p = false; continue; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(c->devs[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) c->p2p = false;
+            cudaGetLastError();
+        }
+    }
+    cudaSetDevice(prev);
     *comm = c;
     return YH_OK;
 }
@@ -107,9 +117,34 @@ extern "C" int yh_comm_destroy(void *comm)
 {
     if (!comm) return YH_OK;
     Comm *c = static_cast<Comm *>(comm);
-    for (ncclComm_t k : c->comms)
-        if (k) g_nccl.CommDestroy(k);
+    for (int i = 0; i < c->ndev; ++i) {
+        if (c->comms[i]) g_nccl.CommDestroy(static_cast<ncclComm_t>(c->comms[i]));
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    }
     delete c;
+    return YH_OK;
+}
+
+extern "C" int yh_comm_p2p(void *comm) { return (comm && static_cast<Comm *>(comm)->p2p) ? 1 : 0; }
+
+// Cross-device barrier on the devices' streams (no host wait): everything enqueued so far on every stream
+// happens before anything enqueued afterwards on any of them.
+extern "C" int yh_comm_barrier(void *comm, void *const *streams)
+{
+    YH_REQUIRE(comm != nullptr, "comm_barrier: null communicator");
+    Comm *c = static_cast<Comm *>(comm);
+    int prev = 0;
+    YH_CUDA(cudaGetDevice(&prev));
+    struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+    for (int d = 0; d < c->ndev; ++d) {
+        YH_CUDA(cudaSetDevice(c->devs[d]));
+        YH_CUDA(cudaEventRecord(c->ev[d], streams ? static_cast<cudaStream_t>(streams[d]) : nullptr));
+    }
+    for (int d = 0; d < c->ndev; ++d) {
+        YH_CUDA(cudaSetDevice(c->devs[d]));
+        for (int e = 0; e < c->ndev; ++e)
+            if (e != d) YH_CUDA(cudaStreamWaitEvent(streams ? static_cast<cudaStream_t>(streams[d]) : nullptr, c->ev[e], 0));
+    }
     return YH_OK;
 }
 
@@ -141,15 +176,15 @@ extern "C" int yh_map_allgather(void *comm, const uint64_t *const *keys, const u
         if (nrec[r] > 0) {
             for (int d = 0; d < c->ndev; ++d) {
                 cudaStream_t st = streams ? static_cast<cudaStream_t>(streams[d]) : nullptr;
-                YH_NCCL(g_nccl.Broadcast(keys[r], out_keys[d] + off, static_cast<size_t>(nrec[r]), kNcclUint64, r, c->comms[d], st));
-                YH_NCCL(g_nccl.Broadcast(tp[r], out_tp[d] + off, static_cast<size_t>(nrec[r]), kNcclUint8, r, c->comms[d], st));
+                YH_NCCL(g_nccl.Broadcast(keys[r], out_keys[d] + off, static_cast<size_t>(nrec[r]), kNcclUint64, r, static_cast<ncclComm_t>(c->comms[d]), st));
+                YH_NCCL(g_nccl.Broadcast(tp[r], out_tp[d] + off, static_cast<size_t>(nrec[r]), kNcclUint8, r, static_cast<ncclComm_t>(c->comms[d]), st));
             }
         }
         off += nrec[r];
     }
     for (int d = 0; d < c->ndev; ++d) {
         cudaStream_t st = streams ? static_cast<cudaStream_t>(streams[d]) : nullptr;
-        YH_NCCL(g_nccl.AllReduce(gt_per_class[d], gt_per_class[d], static_cast<size_t>(C), kNcclInt32, kNcclSum, c->comms[d], st));
+        YH_NCCL(g_nccl.AllReduce(gt_per_class[d], gt_per_class[d], static_cast<size_t>(C), kNcclInt32, kNcclSum, static_cast<ncclComm_t>(c->comms[d]), st));
     }
     YH_NCCL(g_nccl.GroupEnd());
     return YH_OK;

@@ -34,6 +34,16 @@ void count_launch(int n = 1);
         ::yh::count_launch();                                          \
     } while (0)
 
+// communicator of the single-process multi-GPU API (yh_comm.cu, yh_map.cu); comms are ncclComm_t
+constexpr int kMaxPeers = 16;
+struct Comm {
+    int ndev = 0;
+    int devs[kMaxPeers] = {};
+    void *comms[kMaxPeers] = {};
+    cudaEvent_t ev[kMaxPeers] = {};
+    bool p2p = false;       // every device can read/write every other device's memory (NVLink / NVSwitch)
+};
+
 inline int sm_count()
 {
     static int cached[64] = {0};

@@ -116,6 +116,40 @@ __global__ void tp_kernel(const int32_t *__restrict__ hit, const uint32_t *__res
     tp[s] = (h >= 0 && claim[h] == static_cast<uint32_t>(s)) ? 1 : 0;   // utils.py:408-418
 }
 
+// K6d', fused with the exchange step: the TP decision of a detection and its sort key are stored straight into the
+// record buffers of EVERY device of the box (peer-mapped memory over NVLink / NVSwitch) at this shard's offset, so
+// no separate all-gather runs afterwards.  The sorted keys already sit in the local buffer (the radix sort wrote them).
+struct PeerSet {
+    int n, self;
+    uint64_t *keys[kMaxPeers];
+    uint8_t *tp[kMaxPeers];
+    int32_t *gt[kMaxPeers];
+    int64_t offset;
+};
+
+__global__ void tp_scatter_kernel(const int32_t *__restrict__ hit, const uint32_t *__restrict__ claim, int64_t np, PeerSet ps)
+{
+    const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (s >= np) return;
+    const int32_t h = hit[s];
+    const uint8_t tp = (h >= 0 && claim[h] == static_cast<uint32_t>(s)) ? 1 : 0;   // utils.py:408-418
+    const uint64_t key = ps.keys[ps.self][ps.offset + s];
+    for (int d = 0; d < ps.n; ++d) {
+        ps.tp[d][ps.offset + s] = tp;
+        if (d != ps.self) ps.keys[d][ps.offset + s] = key;
+    }
+}
+
+// per-class ground-truth counts of this shard added into every device's accumulator (system-scope atomics)
+__global__ void gt_scatter_kernel(const int32_t *__restrict__ gt_local, int C, PeerSet ps)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int v = gt_local[c];
+    if (v == 0) return;
+    for (int d = 0; d < ps.n; ++d) atomicAdd_system(ps.gt[d] + c, v);
+}
+
 // K7: class segment starts in the sorted record keys: start[c] = lower_bound(c << 32), c = 0..C
 __global__ void class_starts_kernel(const uint64_t *__restrict__ keys, int64_t n, int C, int64_t *__restrict__ start)
 {
@@ -247,16 +281,14 @@ static int bits_for(int C)
 
 using namespace yh;
 
-extern "C" int yh_map_match(const float *true_rows, int64_t nt, const float *pred_rows, int64_t np, int C, float iou_thr,
-                            uint64_t *out_keys, uint8_t *out_tp, int32_t *out_gt_per_class, void *stream)
+static int map_match_impl(const float *true_rows, int64_t nt, const float *pred_rows, int64_t np, int C, float iou_thr,
+                          uint64_t *out_keys, uint8_t *out_tp, int32_t *out_gt_per_class, void *stream, const PeerSet *peers)
 {
     YH_REQUIRE(C >= 1 && nt >= 0 && np >= 0, "map_match: bad sizes");
     YH_REQUIRE(nt < (1ll << 31) && np < (1ll << 31), "map_match: more than 2^31 rows");
     YH_REQUIRE(out_gt_per_class != nullptr, "map_match: out_gt_per_class is null");
     YH_REQUIRE((nt == 0 || true_rows) && (np == 0 || (pred_rows && out_keys && out_tp)), "map_match: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
-    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
     { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
     YH_CUDA(cudaMemsetAsync(out_gt_per_class, 0, sizeof(int32_t) * C, st));
     const int end_bit = bits_for(C);
@@ -270,6 +302,10 @@ extern "C" int yh_map_match(const float *true_rows, int64_t nt, const float *pre
         gt_keys_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(true_rows, nt, C, gk_in.as<uint64_t>(), gv_in.as<uint32_t>(),
                                                             out_gt_per_class);
         YH_LAUNCH_CHECK("gt_keys_kernel");
+    }
+    if (peers) {
+        gt_scatter_kernel<<<blocks_for(C, 128), 128, 0, st>>>(out_gt_per_class, C, *peers);
+        YH_LAUNCH_CHECK("gt_scatter_kernel");
     }
     if (np == 0) return YH_OK;
     det_keys_kernel<<<blocks_for(np, 256), 256, 0, st>>>(pred_rows, np, C, dk_in.as<uint64_t>(), dv_in.as<uint32_t>());
@@ -296,10 +332,47 @@ extern "C" int yh_map_match(const float *true_rows, int64_t nt, const float *pre
                                                       gk.as<uint64_t>(), gv.as<uint32_t>(), nt, C, iou_thr,
                                                       hit.as<int32_t>(), claim.as<uint32_t>());
     YH_LAUNCH_CHECK("match_kernel");
-    tp_kernel<<<blocks_for(np, 256), 256, 0, st>>>(hit.as<int32_t>(), claim.as<uint32_t>(), np, out_tp);
-    YH_LAUNCH_CHECK("tp_kernel");
+    if (peers) {
+        tp_scatter_kernel<<<blocks_for(np, 256), 256, 0, st>>>(hit.as<int32_t>(), claim.as<uint32_t>(), np, *peers);
+        YH_LAUNCH_CHECK("tp_scatter_kernel");
+    } else {
+        tp_kernel<<<blocks_for(np, 256), 256, 0, st>>>(hit.as<int32_t>(), claim.as<uint32_t>(), np, out_tp);
+        YH_LAUNCH_CHECK("tp_kernel");
+    }
     return YH_OK;
 }
+
+extern "C" int yh_map_match(const float *true_rows, int64_t nt, const float *pred_rows, int64_t np, int C, float iou_thr,
+                            uint64_t *out_keys, uint8_t *out_tp, int32_t *out_gt_per_class, void *stream)
+{
+    return map_match_impl(true_rows, nt, pred_rows, np, C, iou_thr, out_keys, out_tp, out_gt_per_class, stream, nullptr);
+}
+
+// Stage 1 fused with the exchange step (single process, peer-mapped memory): device `dev_index` of the communicator
+// matches its shard and stores its records at [offset, offset + np) of EVERY device's record buffers, and adds its
+// per-class ground-truth counts into every device's accumulator gt_sum_all[d] (zeroed by the caller beforehand).
+extern "C" int yh_map_match_p2p(void *comm, int dev_index, const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
+                                int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
+                                int32_t *const *gt_sum_all, void *stream)
+{
+    YH_REQUIRE(comm != nullptr, "map_match_p2p: null communicator");
+    const Comm *c = static_cast<const Comm *>(comm);
+    YH_REQUIRE(c->p2p, "map_match_p2p: the devices of this communicator cannot access each other's memory; use yh_map_allgather");
+    YH_REQUIRE(dev_index >= 0 && dev_index < c->ndev && offset >= 0, "map_match_p2p: bad device index / offset");
+    YH_REQUIRE(out_keys_all && out_tp_all && gt_sum_all, "map_match_p2p: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PeerSet ps;
+    ps.n = c->ndev; ps.self = dev_index; ps.offset = offset;
+    for (int d = 0; d < c->ndev; ++d) {
+        ps.keys[d] = out_keys_all[d]; ps.tp[d] = out_tp_all[d]; ps.gt[d] = gt_sum_all[d];
+        YH_REQUIRE(ps.gt[d] && (np == 0 || (ps.keys[d] && ps.tp[d])), "map_match_p2p: null buffer for device %d", d);
+    }
+    AsyncBuf gt_local(st);
+    YH_CUDA(gt_local.alloc(sizeof(int32_t) * C));
+    return map_match_impl(true_rows, nt, pred_rows, np, C, iou_thr, ps.keys[dev_index] + offset,
+                          ps.tp[dev_index] + offset, gt_local.as<int32_t>(), stream, &ps);
+}
+
 
 extern "C" int yh_map_reduce(const uint64_t *keys, const uint8_t *tp, int64_t nrec, const int32_t *gt_per_class, int C,
                              float *out_ap, float *out_map, void *stream)
@@ -307,8 +380,6 @@ extern "C" int yh_map_reduce(const uint64_t *keys, const uint8_t *tp, int64_t nr
     YH_REQUIRE(C >= 1 && nrec >= 0 && nrec < (1ll << 31), "map_reduce: bad sizes");
     YH_REQUIRE(gt_per_class && out_map && (nrec == 0 || (keys && tp)), "map_reduce: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
-    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
     { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
     const int end_bit = bits_for(C);
     AsyncBuf sk(st), stp(st), cum(st), start(st), ap(st), tmp(st);
@@ -345,8 +416,6 @@ extern "C" int yh_rows_append(const float *boxes, const int32_t *count, int64_t 
     YH_REQUIRE(boxes && count && row_cursor && (out_capacity == 0 || out_rows), "rows_append: null pointer");
     YH_REQUIRE(n < (1ll << 31), "rows_append: too many images in one call");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
-    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
     { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
     AsyncBuf offs(st), tmp(st);
     YH_CUDA(offs.alloc(8 * n));

@@ -21,7 +21,8 @@ SYMBOLS = (
     "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_ex", "yh_decode_nms_host", "yh_filter_rows", "yh_rows_append",
     "yh_loss", "yh_map_match", "yh_map_reduce",
     "yh_encode_labels", "yh_head_to_f32", "yh_decode_nms_typed", "yh_pixel_boxes",
-    "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_workspace_bytes",
+    "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_comm_p2p", "yh_comm_barrier", "yh_map_match_p2p",
+    "yh_workspace_bytes",
     "yh_iou_dl", "yh_decode_dl", "yh_nms_dl", "yh_decode_nms_dl", "yh_loss_dl",
 )
 
@@ -63,6 +64,9 @@ def lib():
     L.yh_comm_init_all.argtypes = [i, vp, vp]
     L.yh_comm_destroy.argtypes = [vp]
     L.yh_map_allgather.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, i64, vp]
+    L.yh_comm_p2p.argtypes = [vp]
+    L.yh_comm_barrier.argtypes = [vp, vp]
+    L.yh_map_match_p2p.argtypes = [vp, i, vp, i64, vp, i64, i, f, vp, vp, i64, vp, vp]
     L.yh_workspace_bytes.argtypes = [i, i64, i, i, i]
     L.yh_workspace_bytes.restype = C.c_size_t
     L.yh_iou_dl.argtypes = [vp, vp, vp, vp]

@@ -56,9 +56,49 @@ def main():
         with torch.cuda.device(d):
             m, _ = yu.map_reduce(out_k[d], out_t[d], gts[d], CLS)
             vals.append(float(m))
-    _lib.check(L.yh_comm_destroy(comm), "yh_comm_destroy")
     assert all(v == m_single for v in vals), (vals, m_single)
     assert all(torch.equal(out_k[d].cpu(), out_k[0].cpu()) for d in range(ndev))
+
+    # the same exchange fused into stage 1 over peer-mapped memory (yh_map_match_p2p): no collective call
+    p2p = int(L.yh_comm_p2p(comm))
+    if p2p:
+        f32 = lambda t: t.contiguous().float()
+        pk = [torch.zeros(total, dtype=torch.int64, device=f"cuda:{d}") for d in range(ndev)]
+        pt = [torch.full((total,), 7, dtype=torch.uint8, device=f"cuda:{d}") for d in range(ndev)]
+        pg = [torch.zeros(CLS, dtype=torch.int32, device=f"cuda:{d}") for d in range(ndev)]
+        rows = []
+        for d in range(ndev):
+            lo, hi = n * d // ndev, n * (d + 1) // ndev
+            with torch.cuda.device(d):
+                e = yu.MeanAveragePrecision(CLS, 2)
+                e.img_idx = 0
+                e.update_state(torch.from_numpy(yt[lo:hi]).cuda(d), torch.from_numpy(yp[lo:hi]).cuda(d))
+                rows.append((f32(e.all_true_boxes_variable), f32(e.all_pred_boxes_variable)))
+        for d in range(ndev):
+            torch.cuda.synchronize(d)
+        _lib.check(L.yh_comm_barrier(comm, streams), "yh_comm_barrier")
+        off = 0
+        for d in range(ndev):
+            tr, pr = rows[d]
+            assert pr.shape[0] == nrec[d]
+            with torch.cuda.device(d):
+                _lib.check(L.yh_map_match_p2p(comm, d, tr.data_ptr(), tr.shape[0], pr.data_ptr(), pr.shape[0], CLS, 0.5,
+                                              arr(pk), arr(pt), off, arr(pg), streams[d]), "yh_map_match_p2p")
+            off += nrec[d]
+        _lib.check(L.yh_comm_barrier(comm, streams), "yh_comm_barrier")
+        pvals = []
+        for d in range(ndev):
+            with torch.cuda.device(d):
+                m, _ = yu.map_reduce(pk[d], pt[d], pg[d], CLS)
+                pvals.append(float(m))
+        assert all(v == m_single for v in pvals), (pvals, m_single)
+        for d in range(ndev):
+            assert torch.equal(pk[d].cpu(), out_k[0].cpu()) and torch.equal(pt[d].cpu(), out_t[0].cpu()), d
+            assert torch.equal(pg[d].cpu(), gts[0].cpu()), d
+        print(f"  peer-scatter path (yh_map_match_p2p, no collective): records and mAP identical on all {ndev} devices")
+    else:
+        print("  devices cannot peer-access each other: yh_map_match_p2p not checked")
+    _lib.check(L.yh_comm_destroy(comm), "yh_comm_destroy")
     print(f"multigpu_capi_check ok: {ndev} devices in one process, {total} records, mAP {vals[0]:.9f} == single-GPU {m_single:.9f}")
 
 
