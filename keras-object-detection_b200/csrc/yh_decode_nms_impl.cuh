@@ -435,11 +435,16 @@ __device__ __forceinline__ void decode_cell(const E *__restrict__ p, const NmsCf
             v[2 * i] = x.x;
             v[2 * i + 1] = x.y;
         }
-        cls = 0;
+        // first maximum (tf.argmax, utils.py:173): the maximum by a tree of 3-input FMNMX, then the lowest index
+        // holding it, found by a descending chain of predicated moves (2 instructions per class instead of 3)
         float best = v[0];
 #pragma unroll
-        for (int j = 1; j < CT; ++j)
-            if (v[j] > best) { best = v[j]; cls = j; }            // first max (tf.argmax)
+        for (int j = 1; j + 1 < CT; j += 2) best = fmaxf(fmaxf(best, v[j]), v[j + 1]);
+        if constexpr (CT % 2 == 0) best = fmaxf(best, v[CT - 1]);
+        cls = CT - 1;
+#pragma unroll
+        for (int j = CT - 2; j >= 0; --j)
+            if (v[j] == best) cls = j;
         cbest = best;
         conf = v[CT]; bx = v[CT + 1]; by = v[CT + 2]; bw = v[CT + 3]; bh = v[CT + 4];
 #pragma unroll

@@ -433,6 +433,45 @@ def test_cfg2_full_size_one_million_images(dev):
     assert 39.0 < kept / 1e6 < 41.0
 
 
+def test_more_than_2_pow_31_elements(dev):
+    """64-bit addressing: 1.6 M VOC images = 2.35e9 input elements (> 2**31); the tail of the batch (elements past
+    the 32-bit limit) is audited against the C port, decode / loss / gradient there against a run on the tail alone."""
+    from yolohot import utils as yu, loss as yl
+    n, audit = 1_600_000, 4096
+    g = torch.Generator(device=dev)
+    g.manual_seed(77)
+    p = torch.rand((n, 7, 7, 30), generator=g, device=dev)
+    assert p.numel() > 2 ** 31
+    boxes, cnt, kidx = yu.decode_nms(p, 20, 2, 0.5, 0.4, return_index=True)
+    for lo in (0, n - audit):
+        want = cport.decode_nms(p[lo:lo + audit].cpu().numpy(), 20, 2, 0.5, 0.4, nthreads=cport.num_threads())
+        _check_nms((boxes[lo:lo + audit], cnt[lo:lo + audit], kidx[lo:lo + audit]), want, f"2^31 slice@{lo}")
+    tb, tc, tk = yu.decode_nms(p[n - 300_000:], 20, 2, 0.5, 0.4, return_index=True)
+    assert torch.equal(tc, cnt[n - 300_000:])
+    mt = torch.arange(49, device=dev)[None, :] < tc[:, None]
+    assert torch.equal(tb[mt], boxes[n - 300_000:][mt]) and torch.equal(tk[mt], kidx[n - 300_000:][mt])
+    del boxes, kidx, tb, tk, mt
+    d_all = yu.decode_predictions(p, 20, 2)
+    assert torch.equal(d_all[n - audit:], yu.decode_predictions(p[n - audit:], 20, 2))
+    del d_all
+    # loss: label grids = thresholded copies of the predictions' own layout (any y_true works for an addressing check)
+    t = torch.zeros_like(p)
+    obj = p[..., 20] > 0.9
+    t[..., 20] = obj.float()
+    t[..., 21:25] = p[..., 25:29] * obj[..., None]
+    t[..., 3] = obj.float()
+    terms, grad = yl.yolo_v1_loss_terms(t, p, grad=True)
+    parts = torch.zeros(6, dtype=torch.float64, device=dev)
+    step = 400_000
+    for lo in range(0, n, step):
+        parts += yl.yolo_v1_loss_terms(t[lo:lo + step], p[lo:lo + step]).double()
+    np.testing.assert_allclose(terms.cpu().numpy(), parts.cpu().numpy(), rtol=2e-5)
+    _, g_tail = yl.yolo_v1_loss_terms(t[n - audit:], p[n - audit:], grad=True)
+    assert torch.equal(grad[n - audit:], g_tail)                         # the sum's gradient is per cell
+    want = cport.loss(t[n - audit:].cpu().numpy(), p[n - audit:].cpu().numpy(), 20, 2)
+    np.testing.assert_allclose(yl.yolo_v1_loss_terms(t[n - audit:], p[n - audit:]).cpu().numpy(), want, rtol=1e-5)
+
+
 def test_cfg5_full_size_stress(dev):
     """BASELINE configs[4]: S=14 B=3 C=80, conf threshold 0.05, 131,072 images (9.76 GB), big-image kernel."""
     from yolohot import utils as yu
