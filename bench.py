@@ -313,6 +313,26 @@ def run_own(args):
            "ms_per_step": 1000.0 * e2e_s, "api": "yh_decode_nms_host (C-ABI, pinned host buffers in/out)",
            "counts_match_device_path": ok_e2e, "numa_binding_rank0": numa, "bare_pinned_h2d_copy_GBps": h2d_gbs,
            "frac_of_bare_h2d_copy": (e2e_n * IMG_IN / e2e_s / 1e9) / h2d_gbs}
+    # the same call with a float16 head (half the bytes over PCIe; widened exactly inside the kernel) - context only,
+    # the headline e2e above stays on the reference's float32 tensors
+    e2e_half = None
+    if world == 1 and env_int("YH_BENCH_E2E_HALF", 1):
+        h_half = torch.empty((e2e_n, S, S, D), dtype=torch.float16, pin_memory=True)
+        h_half.copy_(h_in)
+
+        def half_step():
+            _lib.check(L.yh_decode_nms_host_typed(h_half.data_ptr(), _lib.YH_DTYPE_F16, e2e_n, S, B, C, IOU_THR, CONF_THR,
+                                                  h_boxes.data_ptr(), h_cnt.data_ptr(), None, local), "yh_decode_nms_host_typed")
+        half_step()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            half_step()
+        torch.cuda.synchronize(dev)
+        hs = (time.perf_counter() - t0) / e2e_steps
+        e2e_half = {"value": e2e_n / hs, "unit": UNIT, "ms_per_step": 1000.0 * hs, "h2d_bytes_per_step": e2e_n * IMG_IN // 2,
+                    "api": "yh_decode_nms_host_typed (float16 head, pinned host buffers)",
+                    "note": "float16 rounding of the synthetic inputs changes the results; parity is against the widened tensor"}
+        del h_half
     del h_in, h_boxes
 
     # ---- CPU baseline (rank 0, N=1 only): oracle C port on a bounded slice of the same inputs
@@ -357,6 +377,8 @@ def run_own(args):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_job, "clocks": clocks,
     }
     line.update(extras)
+    if e2e_half is not None:
+        line["e2e_float16_head"] = e2e_half
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

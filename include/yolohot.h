@@ -202,6 +202,13 @@ YH_API int yh_decode_nms_typed(const void *pred, int dtype, int64_t n, int S, in
                         float iou_thr, float conf_thr, int score_mode,
                         float *out_boxes, int32_t *out_count, int32_t *out_keep_idx, void *stream);
 
+/* yh_decode_nms_host for a HOST tensor of element type `dtype`: a float16 / bfloat16 head crosses PCIe and HBM at
+ * half the bytes and is widened exactly inside the kernel (results = yh_decode_nms_host on the widened tensor). */
+YH_API int yh_decode_nms_host_typed(const void *pred_host, int dtype, int64_t n, int S, int B, int C,
+                             float iou_thr, float conf_thr,
+                             float *out_boxes_host, int32_t *out_count_host,
+                             int32_t *out_keep_idx_host /* nullable */, int device);
+
 /* N4 - utils.py:652-655 (get_tagged_img / get_grid_tagged_img): pixel corners of kept rows,
  * xmin = int((cx - w/2) * width), ... in float32, int() truncating toward zero.
  * rows (n, M, 6) as written by yh_nms / yh_decode_nms, count (n) nullable; out (n, M, 4) int32

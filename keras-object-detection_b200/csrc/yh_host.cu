@@ -44,9 +44,12 @@ static int grow(void **p, size_t &cap, size_t need, bool &changed)
 
 using namespace yh;
 
-extern "C" int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
-                                  float *out_boxes_host, int32_t *out_count_host, int32_t *out_keep_idx_host, int device)
+static int host_impl(const void *pred_host_v, int dtype, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
+                     float *out_boxes_host, int32_t *out_count_host, int32_t *out_keep_idx_host, int device)
 {
+    YH_REQUIRE(dtype == YH_DTYPE_F32 || dtype == YH_DTYPE_F16 || dtype == YH_DTYPE_BF16, "decode_nms_host: unknown dtype %d", dtype);
+    const int64_t esize = dtype == YH_DTYPE_F32 ? 4 : 2;
+    const unsigned char *pred_host = static_cast<const unsigned char *>(pred_host_v);
     YH_REQUIRE(n >= 0 && S >= 1 && B >= 1 && C >= 1, "decode_nms_host: bad sizes");
     YH_REQUIRE(device >= 0 && device < 64, "decode_nms_host: bad device %d", device);
     if (n == 0) return YH_OK;
@@ -58,7 +61,7 @@ extern "C" int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int 
     struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
 
     const int64_t M = static_cast<int64_t>(S) * S, D = C + 5 * B;
-    const int64_t img_in = 4 * M * D, img_boxes = 4 * M * 6;
+    const int64_t img_in = esize * M * D, img_boxes = 4 * M * 6;
     // chunk: ~96 MiB of input, a multiple of 16 images so every chunk keeps the TMA alignment
     int64_t chunk = std::max<int64_t>(16, ((96ll << 20) / img_in) & ~15ll);
     chunk = std::min<int64_t>(chunk, (n + 15) & ~15ll);
@@ -88,9 +91,13 @@ extern "C" int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int 
         const int s = static_cast<int>(c % kSlots);
         const int64_t cnt = std::min(chunk, n - lo);
         cudaStream_t st = cx.st[s];
-        YH_CUDA(cudaMemcpyAsync(cx.d_in[s], pred_host + lo * M * D, cnt * img_in, cudaMemcpyHostToDevice, st));
-        rc = decode_nms_device(cx.d_in[s], cnt, S, B, C, iou_thr, conf_thr, cx.d_boxes[s], cx.d_count[s],
-                               out_keep_idx_host ? cx.d_idx[s] : nullptr, st, YH_SCORE_CONF);
+        YH_CUDA(cudaMemcpyAsync(cx.d_in[s], pred_host + lo * img_in, cnt * img_in, cudaMemcpyHostToDevice, st));
+        if (dtype == YH_DTYPE_F32)
+            rc = decode_nms_device(cx.d_in[s], cnt, S, B, C, iou_thr, conf_thr, cx.d_boxes[s], cx.d_count[s],
+                                   out_keep_idx_host ? cx.d_idx[s] : nullptr, st, YH_SCORE_CONF);
+        else        // float16 / bfloat16 head: half the bytes over PCIe and HBM, widened exactly inside the kernel
+            rc = yh_decode_nms_typed(cx.d_in[s], dtype, cnt, S, B, C, iou_thr, conf_thr, YH_SCORE_CONF, cx.d_boxes[s],
+                                     cx.d_count[s], out_keep_idx_host ? cx.d_idx[s] : nullptr, st);
         if (rc != YH_OK) break;
         YH_CUDA(cudaMemcpyAsync(out_boxes_host + lo * M * 6, cx.d_boxes[s], cnt * img_boxes, cudaMemcpyDeviceToHost, st));
         YH_CUDA(cudaMemcpyAsync(out_count_host + lo, cx.d_count[s], cnt * 4, cudaMemcpyDeviceToHost, st));
@@ -102,4 +109,17 @@ extern "C" int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int 
         if (e != cudaSuccess && rc == YH_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
     }
     return rc;
+}
+
+extern "C" int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int B, int C, float iou_thr, float conf_thr,
+                                  float *out_boxes_host, int32_t *out_count_host, int32_t *out_keep_idx_host, int device)
+{
+    return host_impl(pred_host, YH_DTYPE_F32, n, S, B, C, iou_thr, conf_thr, out_boxes_host, out_count_host, out_keep_idx_host, device);
+}
+
+extern "C" int yh_decode_nms_host_typed(const void *pred_host, int dtype, int64_t n, int S, int B, int C, float iou_thr,
+                                        float conf_thr, float *out_boxes_host, int32_t *out_count_host,
+                                        int32_t *out_keep_idx_host, int device)
+{
+    return host_impl(pred_host, dtype, n, S, B, C, iou_thr, conf_thr, out_boxes_host, out_count_host, out_keep_idx_host, device);
 }

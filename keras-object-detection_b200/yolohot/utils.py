@@ -139,23 +139,33 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
         raise ValueError(f"decode_nms: score_mode must be 'conf' or 'conf_x_prob', got {score_mode!r}")
     if score_mode != "conf" and (isinstance(predictions, np.ndarray) or not (isinstance(predictions, torch.Tensor) or hasattr(predictions, "__dlpack__"))):
         predictions = torch.from_numpy(np.ascontiguousarray(np.asarray(predictions, dtype=np.float32))).cuda()
-    if not isinstance(predictions, torch.Tensor) and not hasattr(predictions, "__dlpack__") or isinstance(predictions, np.ndarray):
+    host_half = (score_mode == "conf" and isinstance(predictions, torch.Tensor) and not predictions.is_cuda
+                 and predictions.dtype in (torch.float16, torch.bfloat16))
+    if host_half or not isinstance(predictions, torch.Tensor) and not hasattr(predictions, "__dlpack__") or isinstance(predictions, np.ndarray):
         require_cuda()
-        p = np.ascontiguousarray(np.asarray(predictions, dtype=np.float32))
+        # element type on the wire: float16 NumPy arrays and float16 / bfloat16 CPU tensors stay half (yh_decode_nms_host_typed)
+        if host_half:
+            p = predictions.contiguous()
+            code = _lib.YH_DTYPE_F16 if p.dtype == torch.float16 else _lib.YH_DTYPE_BF16
+        elif isinstance(predictions, np.ndarray) and predictions.dtype == np.float16:
+            p, code = np.ascontiguousarray(predictions), _lib.YH_DTYPE_F16
+        else:
+            p, code = np.ascontiguousarray(np.asarray(predictions, dtype=np.float32)), _lib.YH_DTYPE_F32
         if p.ndim == 2:                                   # flat head output (train.py:208)
             D_ = num_classes + 5 * num_boxes
             S_ = int(grid) if grid is not None else int(round((p.shape[1] / D_) ** 0.5))
             if S_ >= 1 and S_ * S_ * D_ == p.shape[1]:
                 p = p.reshape(p.shape[0], S_, S_, D_)
         if p.ndim != 4 or p.shape[1] != p.shape[2] or p.shape[3] != num_classes + 5 * num_boxes:
-            raise ValueError(f"expected (N, S, S, {num_classes + 5 * num_boxes}) predictions, got {p.shape}")
+            raise ValueError(f"expected (N, S, S, {num_classes + 5 * num_boxes}) predictions, got {tuple(p.shape)}")
         n, S = p.shape[0], p.shape[1]
         boxes = np.zeros((n, S * S, 6), np.float32)
         cnt = np.zeros((n,), np.int32)
         kidx = np.full((n, S * S), -1, np.int32) if return_index else None
-        _lib.check(L.yh_decode_nms_host(p.ctypes.data, n, S, int(num_boxes), int(num_classes), float(iou_threshold),
-                                        float(conf_threshold), boxes.ctypes.data, cnt.ctypes.data,
-                                        kidx.ctypes.data if return_index else None, torch.cuda.current_device()),
+        src = p.data_ptr() if host_half else p.ctypes.data
+        _lib.check(L.yh_decode_nms_host_typed(src, code, n, S, int(num_boxes), int(num_classes), float(iou_threshold),
+                                              float(conf_threshold), boxes.ctypes.data, cnt.ctypes.data,
+                                              kidx.ctypes.data if return_index else None, torch.cuda.current_device()),
                    "decode_nms")
         return (boxes, cnt, kidx) if return_index else (boxes, cnt)
     half = isinstance(predictions, torch.Tensor) and predictions.is_cuda and predictions.dtype in (torch.float16, torch.bfloat16)

@@ -205,6 +205,13 @@ def test_decode_nms_host_entry(dev):
     _check_nms(got, want, "host")
     pin = torch.from_numpy(p[:5001]).pin_memory().numpy()
     _check_nms(yu.decode_nms(pin, 20, 2, return_index=True), tuple(w[:5001] for w in want), "host-pinned")
+    # half-precision heads stay half on the wire (yh_decode_nms_host_typed): equal to the float32 path on the widened tensor
+    for h in (p[:30001].astype(np.float16), torch.from_numpy(p[:30001]).to(torch.bfloat16)):
+        wide = h.astype(np.float32) if isinstance(h, np.ndarray) else h.float().numpy()
+        wantw = cport.decode_nms(wide, 20, 2, nthreads=cport.num_threads())
+        goth = yu.decode_nms(h, 20, 2, return_index=True)
+        assert all(isinstance(x, np.ndarray) for x in goth)
+        _check_nms(goth, wantw, "host-half")
 
 
 def test_decode_nms_large_vs_cport_and_properties(dev):
