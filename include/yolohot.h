@@ -167,6 +167,23 @@ YH_API int yh_map_match_p2p(void *comm, int dev_index, const float *true_rows, i
                      int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
                      int32_t *const *gt_sum_all, void *stream);
 
+/* The same fused stage for ANY set of peer-mapped buffers - e.g. one process per GPU, buffers of the other processes
+ * mapped through CUDA IPC (yh_ipc_*): this device is peer `self` of `n_peers`.  gt_sum_all may be NULL (no system
+ * atomics; the shard's own counts go to out_gt_local and the caller sums them, e.g. with the all-reduce that also
+ * orders the peers' stores before the reduce stage); out_gt_local may be NULL when gt_sum_all is given. */
+YH_API int yh_map_match_peers(int n_peers, int self, const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
+                       int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
+                       int32_t *const *gt_sum_all, int32_t *out_gt_local, void *stream);
+
+/* Device buffers that other processes of the same box can map: yh_ipc_alloc = cudaMalloc (zero-filled) + an opaque
+ * YH_IPC_HANDLE_BYTES handle to send to the peers; yh_ipc_open maps a peer's handle (never one's own) with peer access
+ * over NVLink; yh_ipc_close unmaps; yh_ipc_free releases an own buffer after every peer closed it. */
+#define YH_IPC_HANDLE_BYTES 64
+YH_API int yh_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle);
+YH_API int yh_ipc_open(const unsigned char *handle, void **ptr);
+YH_API int yh_ipc_close(void *ptr);
+YH_API int yh_ipc_free(void *ptr);
+
 /* Device scratch (bytes) an operation allocates internally for n images / rows; informational. */
 #define YH_OP_DECODE_NMS 1
 #define YH_OP_DECODE_NMS_HOST 2

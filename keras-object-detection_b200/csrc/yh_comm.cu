@@ -12,6 +12,8 @@
 #include <mutex>
 #include <vector>
 
+#include <string.h>
+
 #include "yh_common.cuh"
 
 namespace yh {
@@ -208,4 +210,48 @@ extern "C" size_t yh_workspace_bytes(int op, int64_t n, int S, int B, int C)
         case YH_OP_MAP_REDUCE: return static_cast<size_t>(n) * 40 + (1u << 20);
         default: return 0;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// One process per GPU: record buffers other processes of the box can map (CUDA IPC), so that a rank's match
+// kernel stores straight into every peer's buffer (yh_map_match_peers) instead of all-gathering afterwards.
+// ------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == YH_IPC_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int yh_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle)
+{
+    YH_REQUIRE(ptr && handle && bytes > 0, "ipc_alloc: bad arguments");
+    *ptr = nullptr;
+    YH_CUDA(cudaMalloc(ptr, bytes));               // a whole cudaMalloc allocation: the handle maps exactly this range
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e == cudaSuccess) e = cudaMemset(*ptr, 0, bytes);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        return cuda_fail(e, "cudaIpcGetMemHandle");
+    }
+    memcpy(handle, &h, sizeof(h));
+    return YH_OK;
+}
+
+extern "C" int yh_ipc_open(const unsigned char *handle, void **ptr)
+{
+    YH_REQUIRE(ptr && handle, "ipc_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    YH_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return YH_OK;
+}
+
+extern "C" int yh_ipc_close(void *ptr)
+{
+    if (ptr) YH_CUDA(cudaIpcCloseMemHandle(ptr));
+    return YH_OK;
+}
+
+extern "C" int yh_ipc_free(void *ptr)
+{
+    if (ptr) YH_CUDA(cudaFree(ptr));
+    return YH_OK;
 }

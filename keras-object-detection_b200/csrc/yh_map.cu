@@ -125,6 +125,7 @@ struct PeerSet {
     uint8_t *tp[kMaxPeers];
     int32_t *gt[kMaxPeers];
     int64_t offset;
+    int has_gt;
 };
 
 __global__ void tp_scatter_kernel(const int32_t *__restrict__ hit, const uint32_t *__restrict__ claim, int64_t np, PeerSet ps)
@@ -303,7 +304,7 @@ static int map_match_impl(const float *true_rows, int64_t nt, const float *pred_
                                                             out_gt_per_class);
         YH_LAUNCH_CHECK("gt_keys_kernel");
     }
-    if (peers) {
+    if (peers && peers->has_gt) {
         gt_scatter_kernel<<<blocks_for(C, 128), 128, 0, st>>>(out_gt_per_class, C, *peers);
         YH_LAUNCH_CHECK("gt_scatter_kernel");
     }
@@ -348,9 +349,37 @@ extern "C" int yh_map_match(const float *true_rows, int64_t nt, const float *pre
     return map_match_impl(true_rows, nt, pred_rows, np, C, iou_thr, out_keys, out_tp, out_gt_per_class, stream, nullptr);
 }
 
-// Stage 1 fused with the exchange step (single process, peer-mapped memory): device `dev_index` of the communicator
-// matches its shard and stores its records at [offset, offset + np) of EVERY device's record buffers, and adds its
-// per-class ground-truth counts into every device's accumulator gt_sum_all[d] (zeroed by the caller beforehand).
+// Stage 1 fused with the exchange step over peer-mapped memory: this device (index `self` of `n_peers`) matches its
+// shard and stores its records at [offset, offset + np) of EVERY peer's record buffers.  The pointers may come from
+// cudaDeviceEnablePeerAccess in one process (yh_map_match_p2p) or from CUDA IPC handles of other processes (yh_ipc_open).
+// gt_sum_all (nullable): per-device accumulators that receive this shard's per-class GT counts by system-scope atomics;
+// out_gt_local (nullable): the shard's own counts (for a caller that sums them itself).
+extern "C" int yh_map_match_peers(int n_peers, int self, const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
+                                  int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
+                                  int32_t *const *gt_sum_all, int32_t *out_gt_local, void *stream)
+{
+    YH_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && self >= 0 && self < n_peers && offset >= 0,
+               "map_match_peers: bad peer count / index / offset (at most %d peers)", kMaxPeers);
+    YH_REQUIRE(C >= 1 && out_keys_all && out_tp_all, "map_match_peers: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PeerSet ps;
+    ps.n = n_peers; ps.self = self; ps.offset = offset;
+    for (int d = 0; d < n_peers; ++d) {
+        ps.keys[d] = out_keys_all[d]; ps.tp[d] = out_tp_all[d]; ps.gt[d] = gt_sum_all ? gt_sum_all[d] : nullptr;
+        YH_REQUIRE((!gt_sum_all || ps.gt[d]) && (np == 0 || (ps.keys[d] && ps.tp[d])), "map_match_peers: null buffer for peer %d", d);
+    }
+    ps.has_gt = gt_sum_all ? 1 : 0;
+    AsyncBuf gt_tmp(st);
+    int32_t *gt_local = out_gt_local;
+    if (!gt_local) {
+        YH_CUDA(gt_tmp.alloc(sizeof(int32_t) * C));
+        gt_local = gt_tmp.as<int32_t>();
+    }
+    return map_match_impl(true_rows, nt, pred_rows, np, C, iou_thr, ps.keys[self] + offset, ps.tp[self] + offset, gt_local,
+                          stream, &ps);
+}
+
+// Single-process flavour: the peers are the devices of a communicator (peer access enabled by yh_comm_init_all).
 extern "C" int yh_map_match_p2p(void *comm, int dev_index, const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
                                 int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
                                 int32_t *const *gt_sum_all, void *stream)
@@ -358,21 +387,10 @@ extern "C" int yh_map_match_p2p(void *comm, int dev_index, const float *true_row
     YH_REQUIRE(comm != nullptr, "map_match_p2p: null communicator");
     const Comm *c = static_cast<const Comm *>(comm);
     YH_REQUIRE(c->p2p, "map_match_p2p: the devices of this communicator cannot access each other's memory; use yh_map_allgather");
-    YH_REQUIRE(dev_index >= 0 && dev_index < c->ndev && offset >= 0, "map_match_p2p: bad device index / offset");
-    YH_REQUIRE(out_keys_all && out_tp_all && gt_sum_all, "map_match_p2p: null pointer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PeerSet ps;
-    ps.n = c->ndev; ps.self = dev_index; ps.offset = offset;
-    for (int d = 0; d < c->ndev; ++d) {
-        ps.keys[d] = out_keys_all[d]; ps.tp[d] = out_tp_all[d]; ps.gt[d] = gt_sum_all[d];
-        YH_REQUIRE(ps.gt[d] && (np == 0 || (ps.keys[d] && ps.tp[d])), "map_match_p2p: null buffer for device %d", d);
-    }
-    AsyncBuf gt_local(st);
-    YH_CUDA(gt_local.alloc(sizeof(int32_t) * C));
-    return map_match_impl(true_rows, nt, pred_rows, np, C, iou_thr, ps.keys[dev_index] + offset,
-                          ps.tp[dev_index] + offset, gt_local.as<int32_t>(), stream, &ps);
+    YH_REQUIRE(dev_index >= 0 && dev_index < c->ndev && gt_sum_all, "map_match_p2p: bad device index / null pointer");
+    return yh_map_match_peers(c->ndev, dev_index, true_rows, nt, pred_rows, np, C, iou_thr, out_keys_all, out_tp_all, offset,
+                              gt_sum_all, nullptr, stream);
 }
-
 
 extern "C" int yh_map_reduce(const uint64_t *keys, const uint8_t *tp, int64_t nrec, const int32_t *gt_per_class, int C,
                              float *out_ap, float *out_map, void *stream)

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("YH_LIB_PATH") or os.path.join(_HERE, "libyolohot.so")   # YH_LIB_PATH: A/B builds
 
 YH_OK, YH_ERR_ARG, YH_ERR_CUDA, YH_ERR_NCCL, YH_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+YH_IPC_HANDLE_BYTES = 64
 YH_DTYPE_F32, YH_DTYPE_F16, YH_DTYPE_BF16 = 0, 1, 2
 
 _lib = None
@@ -21,7 +22,8 @@ SYMBOLS = (
     "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_ex", "yh_decode_nms_host", "yh_decode_nms_host_typed", "yh_filter_rows", "yh_rows_append",
     "yh_loss", "yh_map_match", "yh_map_reduce",
     "yh_encode_labels", "yh_head_to_f32", "yh_decode_nms_typed", "yh_pixel_boxes",
-    "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_comm_p2p", "yh_comm_barrier", "yh_map_match_p2p",
+    "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_comm_p2p", "yh_comm_barrier", "yh_map_match_p2p", "yh_map_match_peers",
+    "yh_ipc_alloc", "yh_ipc_open", "yh_ipc_close", "yh_ipc_free",
     "yh_workspace_bytes",
     "yh_iou_dl", "yh_decode_dl", "yh_nms_dl", "yh_decode_nms_dl", "yh_loss_dl",
 )
@@ -68,6 +70,11 @@ def lib():
     L.yh_comm_p2p.argtypes = [vp]
     L.yh_comm_barrier.argtypes = [vp, vp]
     L.yh_map_match_p2p.argtypes = [vp, i, vp, i64, vp, i64, i, f, vp, vp, i64, vp, vp]
+    L.yh_map_match_peers.argtypes = [i, i, vp, i64, vp, i64, i, f, vp, vp, i64, vp, vp, vp]
+    L.yh_ipc_alloc.argtypes = [C.c_size_t, vp, vp]
+    L.yh_ipc_open.argtypes = [vp, vp]
+    L.yh_ipc_close.argtypes = [vp]
+    L.yh_ipc_free.argtypes = [vp]
     L.yh_workspace_bytes.argtypes = [i, i64, i, i, i]
     L.yh_workspace_bytes.restype = C.c_size_t
     L.yh_iou_dl.argtypes = [vp, vp, vp, vp]

@@ -240,10 +240,14 @@ def mean_average_precision(true_boxes, pred_boxes, num_classes, iou_threshold=0.
     p, _ = as_device_f32(pred_boxes, t.device)
     t = t.reshape(-1, 7)
     p = p.reshape(-1, 7)
-    keys, tp, gtc = map_match(t, p, num_classes, iou_threshold)
     from . import dist as _dist
-    if _dist.world_size() > 1:
-        keys, tp, gtc = _dist.gather_records(keys, tp, gtc)
+    ex = _dist.peer_exchange(t.device) if _dist.world_size() > 1 else None
+    if ex is not None:          # ranks of one box: the matching kernel stores its records into every peer's buffer
+        keys, tp, gtc = ex.match_gather(t, p, num_classes, iou_threshold)
+    else:
+        keys, tp, gtc = map_match(t, p, num_classes, iou_threshold)
+        if _dist.world_size() > 1:
+            keys, tp, gtc = _dist.gather_records(keys, tp, gtc)
     m, ap = map_reduce(keys, tp, gtc, num_classes)
     if kind == "numpy":
         m = np.float32(m.item())

@@ -39,6 +39,46 @@ def main():
     k, t, g = yu.map_match(e1.all_true_boxes_variable, e1.all_pred_boxes_variable, 20, 0.5)
     m_single = float(yu.map_reduce(k, t, g, 20)[0])
     assert m_sharded == m_single, (rank, m_sharded, m_single)
+    # the two exchange implementations (yolohot.dist): records stored into the peers' buffers by the matching kernel
+    # (CUDA IPC + NVLink, the default on one box) against the padded NCCL all-gathers - record for record
+    tr, pr = ev.all_true_boxes_variable, ev.all_pred_boxes_variable
+    k, t, g = yu.map_match(tr, pr, 20, 0.5)
+    k_n, t_n, g_n = yd.gather_records(k, t, g)
+    ex = yd.peer_exchange(dev)
+    p2p = ex is not None
+    if os.environ.get("YH_DIST_P2P", "1") != "0":
+        assert p2p, "PeerExchange unavailable on this box"
+    if p2p:
+        for rnd in range(3):                                    # buffer reuse across calls
+            k_p, t_p, g_p = ex.match_gather(tr, pr, 20, 0.5)
+            assert torch.equal(k_p, k_n) and torch.equal(t_p, t_n) and torch.equal(g_p, g_n), (rank, rnd)
+        # latency of the two paths (stage 1 + exchange), wall clock around a device sync, max over ranks
+        import time
+
+        def lat(fn, reps=20):
+            fn()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize(dev)
+            v = torch.tensor([(time.perf_counter() - t0) / reps], device=dev, dtype=torch.float64)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            return float(v) * 1e3
+        ms_peer = lat(lambda: ex.match_gather(tr, pr, 20, 0.5))
+        ms_nccl = lat(lambda: yd.gather_records(*yu.map_match(tr, pr, 20, 0.5)))
+        if rank == 0:
+            print(f"  stage 1 + exchange, {k_n.shape[0]} records, world {world}: peer stores {ms_peer:.3f} ms, "
+                  f"padded NCCL all-gathers {ms_nccl:.3f} ms")
+        small = yd.PeerExchange(dev, capacity=1024)             # forced collective growth of the buffers
+        k_p, t_p, g_p = small.match_gather(tr, pr, 20, 0.5)
+        assert small.capacity >= k_n.shape[0] and torch.equal(k_p, k_n) and torch.equal(t_p, t_n) and torch.equal(g_p, g_n)
+        m_small = float(yu.map_reduce(k_p, t_p, g_p, 20)[0])
+        assert m_small == m_single
+        small.close()
+        empty = ex.match_gather(tr[:0], pr[:0], 20, 0.5)        # no ground truth and no detections anywhere
+        assert empty[0].shape[0] == 0 and int(empty[2].sum()) == 0
     # decode+NMS and loss need no communication: shard results are slices of the whole
     b_all, c_all = yu.decode_nms(torch.from_numpy(yp).to(dev), 20, 2)
     b_sh, c_sh = yu.decode_nms(torch.from_numpy(yp[lo:hi]).to(dev), 20, 2)
@@ -51,7 +91,8 @@ def main():
     dist.all_gather(vals, torch.tensor([m_sharded], device=dev, dtype=torch.float64))
     assert all(float(v) == m_sharded for v in vals)
     if rank == 0:
-        print(f"multigpu_check ok: world={world} mAP sharded={m_sharded:.9f} single={m_single:.9f}")
+        print(f"multigpu_check ok: world={world} mAP sharded={m_sharded:.9f} single={m_single:.9f} "
+              f"exchange={'peer stores (CUDA IPC) == NCCL all-gather' if p2p else 'NCCL all-gather'} records={k_n.shape[0]}")
     dist.destroy_process_group()
 
 
