@@ -257,6 +257,19 @@ def mean_average_precision(true_boxes, pred_boxes, num_classes, iou_threshold=0.
     return (m, ap) if return_ap else m
 
 
+def change_tensor(tensor_1d, idx_col):
+    """utils.py:280-299: copy of a 1-D tensor with element `idx_col` set to 1.  The reference's matching loop keeps
+    its claimed-ground-truth flags with it (utils.py:411); the matching kernel K6 keeps them in device memory instead,
+    so this is only here for callers that import the name."""
+    if isinstance(tensor_1d, torch.Tensor):
+        out = tensor_1d.clone()
+        out[int(idx_col)] = 1
+        return out
+    out = np.array(tensor_1d, copy=True)
+    out[int(idx_col)] = 1
+    return out
+
+
 def mean_average_precision_numpy(true_boxes, pred_boxes, num_classes, iou_threshold=0.5):
     """utils.py:499-585 twin."""
     return mean_average_precision(np.asarray(true_boxes, np.float32), np.asarray(pred_boxes, np.float32),

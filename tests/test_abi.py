@@ -97,13 +97,23 @@ def test_reference_module_names_resolve():
                        "MeanAveragePrecision", "MeanAveragePrecisionNumpy", "get_all_bboxes", "non_max_suppression_2",
                        "mean_average_precision_2", "decode_predictions_numpy", "non_max_suppression_numpy",
                        "intersection_over_union_numpy", "mean_average_precision_numpy"],
-             "loss": ["YoloV1Loss"], "metric": ["MeanAveragePrecision", "MeanAveragePrecision2"]}
+             "loss": ["YoloV1Loss"], "metric": ["MeanAveragePrecision", "MeanAveragePrecision2"],
+             # the single-file variant of the reference (yolo_v1/yolo_v1.py:39,75,112,177,200,355,394,613)
+             "yolo_v1": ["intersection_over_union", "non_max_suppression", "decode_predictions", "change_tensor",
+                         "mean_average_precision", "MeanAveragePrecision", "get_tagged_img", "YoloV1Loss"]}
+    mods = {}
     for mod, syms in names.items():
         spec = importlib.util.spec_from_file_location(f"_shim_{mod}", os.path.join(d, mod + ".py"))
         m = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(m)
         for s in syms:
             assert hasattr(m, s), (mod, s)
+        mods[mod] = m
+    import inspect
+    import numpy as np
+    assert inspect.signature(mods["yolo_v1"].decode_predictions).parameters["num_classes"].default == 20   # yolo_v1.py:112
+    assert inspect.signature(mods["utils"].decode_predictions).parameters["num_classes"].default is inspect.Parameter.empty
+    assert np.array_equal(mods["yolo_v1"].change_tensor(np.zeros(4, np.int32), 2), [0, 0, 1, 0])            # yolo_v1.py:177
     from yolohot.loss import YoloV1Loss
     l = YoloV1Loss()
     assert (l.num_classes, l.num_boxes, l.lambda_coord, l.lambda_noobj, l.name) == (20, 2, 5, 0.5, "YoloV1Loss")
