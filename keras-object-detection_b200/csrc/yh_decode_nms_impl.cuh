@@ -202,10 +202,28 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
             if (((pass_m >> t) & 1u)) dup |= (ws.smeta[r[t]] != ci[t]);
         dup = __any_sync(FULL, dup);
         if (dup) {
-            for (int j = 0; j < n; ++j) {
-                const float k = ws.ckey[j];
+            // Equal confidences keep their candidate order (stable sort, utils.py:98).  The members of a tie group
+            // all computed the rank G of its first member and own the positions G .. G+g-1: in every round the
+            // member with the lowest candidate index still waiting takes the group's next position (shared-memory
+            // atomicMin), the others move one position down.  Rounds = size of the largest tie group.
+            for (int q = lane; q < n; q += 32) ws.smeta[q] = 0x7fffffff;
+            __syncwarp();
+            unsigned pend = pass_m;
+            for (;;) {
 #pragma unroll
-                for (int t = 0; t < NS; ++t) r[t] += (((pass_m >> t) & 1u) && j < ci[t] && k == conf[t]) ? 1 : 0;
+                for (int t = 0; t < NS; ++t)
+                    if ((pend >> t) & 1u) atomicMin(&ws.smeta[r[t]], ci[t]);
+                __syncwarp();
+                unsigned lost = 0u;
+#pragma unroll
+                for (int t = 0; t < NS; ++t) {
+                    if (((pend >> t) & 1u) && ws.smeta[r[t]] != ci[t]) {
+                        lost |= 1u << t;
+                        r[t] += 1;
+                    }
+                }
+                pend = lost;
+                if (!__any_sync(FULL, pend != 0u)) break;
             }
         }
     }
@@ -834,7 +852,17 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const E *__res
         team_sync(bar_id, nthr);
         const bool dup = team_any(bar_id, nthr, pass && smeta[r] != ci);
         if (dup) {                                                 // equal confidences exist: lower source index first
-            for (int j = 0; j < n; ++j) r += (pass && j < ci && ckey[j] == conf) ? 1 : 0;
+            // rounds of shared-memory atomicMin over the positions of each tie group, as in nms_warp
+            if (q < n) smeta[q] = 0x7fffffff;
+            team_sync(bar_id, nthr);
+            bool pend = pass;
+            for (;;) {
+                if (pend) atomicMin(&smeta[r], ci);
+                team_sync(bar_id, nthr);
+                pend = pend && smeta[r] != ci;
+                if (pend) r += 1;
+                if (!team_any(bar_id, nthr, pend)) break;          // its barrier also ends this round's reads
+            }
         }
         // ---- C: scatter to rank order (utils.py:24-32,40); class masks
         if (pass) {
