@@ -37,6 +37,160 @@ __device__ __forceinline__ double warp_sum(double v)
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
+// Box / confidence terms of one "heavy" cell (object, or a non-zero true box) and their gradients.  t, p: the cell's
+// D values of y_true / y_pred (shared or global memory); gc: the cell's gradient row (kGrad only).
+template <bool kGrad>
+__device__ __forceinline__ void heavy_box_terms(const float *t, const float *p, float *gc, const LossCfg &cfg, double &sxy,
+                                                double &swh, double &sob, double &snb)
+{
+    const int C = cfg.C, B = cfg.B;
+    const float obj = t[C];                                           // loss.py:162
+    const float tx = t[C + 1], ty = t[C + 2], tw = t[C + 3], th = t[C + 4];
+    int k = 0;                                                        // loss.py:126-137
+    float u = iou_ref(tx, ty, tw, th, p[C + 1], p[C + 2], p[C + 3], p[C + 4]);
+    for (int b = 1; b < B; ++b) {
+        const float *q = p + C + 5 * b;
+        const float v = iou_ref(tx, ty, tw, th, q[1], q[2], q[3], q[4]);
+        if (v > u) { u = v; k = b; }
+    }
+    const float *q = p + C + 5 * k;
+    const float c = q[0], px = q[1], py = q[2], pw = q[3], ph_ = q[4];
+    const float noobj = __fsub_rn(1.0f, obj);
+    const float z = __fsub_rn(0.0f, c);
+    snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));
+    const float dx = __fsub_rn(tx, px), dy = __fsub_rn(ty, py);
+    sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dx, dx)));    // loss.py:171
+    sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dy, dy)));
+    const float sw = sgn(pw), sh = sgn(ph_);
+    const float rw = __fsqrt_rn(__fadd_rn(fabsf(pw), 1e-6f)), rh = __fsqrt_rn(__fadd_rn(fabsf(ph_), 1e-6f));
+    const float dw = __fsub_rn(__fsqrt_rn(tw), __fmul_rn(sw, rw));    // loss.py:176-178
+    const float dh = __fsub_rn(__fsqrt_rn(th), __fmul_rn(sh, rh));
+    swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dw, dw)));
+    swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dh, dh)));
+    const float e = __fsub_rn(u, c);
+    sob += static_cast<double>(__fmul_rn(obj, __fmul_rn(e, e)));      // loss.py:189
+    if (kGrad) {
+        float g_c = cfg.ln * 2.0f * noobj * c;
+        float g_x = 0.f, g_y = 0.f, g_w = 0.f, g_h = 0.f;
+        if (obj != 0.0f) {
+            // IoU pieces again, with their partial derivatives
+            const float x1n = (tx - tw) * 0.5f, x1x = (tx + tw) * 0.5f;
+            const float y1n = (ty - th) * 0.5f, y1x = (ty + th) * 0.5f;
+            const float x2n = (px - pw) * 0.5f, x2x = (px + pw) * 0.5f;
+            const float y2n = (py - ph_) * 0.5f, y2x = (py + ph_) * 0.5f;
+            const float ddx = fminf(x1x, x2x) - fmaxf(x1n, x2n);
+            const float ddy = fminf(y1x, y2x) - fmaxf(y1n, y2n);
+            const float cw = clip01(ddx), ch = clip01(ddy);
+            const float inter = cw * ch;
+            const float a1 = fabsf((x1x - x1n) * (y1x - y1n));
+            const float w2 = x2x - x2n, h2 = y2x - y2n;
+            const float a2 = fabsf(w2 * h2);
+            const float dn = ((a1 + a2) - inter) + 1e-6f;
+            const float inv = 1.0f / dn;
+            const float du_dI = inv + inter * inv * inv;
+            const float du_da2 = -inter * inv * inv;
+            const float in_x = (ddx >= 0.f && ddx <= 1.f) ? 1.f : 0.f;
+            const float in_y = (ddy >= 0.f && ddy <= 1.f) ? 1.f : 0.f;
+            const float mx = (x2x < x1x) ? 1.f : 0.f, nx = (x2n > x1n) ? 1.f : 0.f;
+            const float my = (y2x < y1x) ? 1.f : 0.f, ny = (y2n > y1n) ? 1.f : 0.f;
+            const float sa = sgn(w2 * h2);
+            const float du_dpx = du_dI * in_x * ch * 0.5f * (mx - nx);
+            const float du_dpy = du_dI * in_y * cw * 0.5f * (my - ny);
+            const float du_dpw = du_dI * in_x * ch * 0.5f * (mx + nx) + du_da2 * sa * h2;
+            const float du_dph = du_dI * in_y * cw * 0.5f * (my + ny) + du_da2 * sa * w2;
+            const float e2 = 2.0f * obj * e;
+            g_c -= e2;
+            g_x = -2.0f * cfg.lc * obj * dx + e2 * du_dpx;
+            g_y = -2.0f * cfg.lc * obj * dy + e2 * du_dpy;
+            g_w = -2.0f * cfg.lc * obj * dw * (sw * sw) / (2.0f * rw) + e2 * du_dpw;
+            g_h = -2.0f * cfg.lc * obj * dh * (sh * sh) / (2.0f * rh) + e2 * du_dph;
+        }
+        float *gq = gc + C + 5 * k;                                   // every other box of the cell stays 0
+        gq[0] = g_c; gq[1] = g_x; gq[2] = g_y; gq[3] = g_w; gq[4] = g_h;
+    }
+}
+
+// Class term of one heavy cell with an object (loss.py:206) by one warp, lanes over classes.
+template <bool kGrad>
+__device__ __forceinline__ void heavy_class_term(const float *t, const float *p, float *gc, int C, int lane, double &scl)
+{
+    const float obj = t[C];
+    if (obj != 0.0f) {
+        for (int j = lane; j < C; j += 32) {
+            const float d = __fsub_rn(t[j], p[j]);
+            scl += static_cast<double>(__fmul_rn(obj, __fmul_rn(d, d)));
+            if (kGrad) gc[j] = -2.0f * obj * d;
+        }
+    }
+}
+
+// Deterministic batch sums: lanes -> warp -> block partials (fixed order); the last block to finish (ticket counter)
+// adds the partials of all blocks in index order and writes the six outputs, so the result does not depend on which
+// block came last.  Called by every thread of the block (>= 128 threads), once.
+constexpr int kLossMaxWarps = 8;
+__device__ __forceinline__ void block_finish(double sxy, double swh, double sob, double snb, double scl, const LossCfg &cfg,
+                                             double *__restrict__ partials, unsigned *__restrict__ ticket,
+                                             float *__restrict__ out_terms)
+{
+    __shared__ double red[kLossMaxWarps][5];
+    __shared__ double fin[5][26];
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    // stage 1 of the deterministic reduction: lanes -> warp -> block, fixed order
+    sxy = warp_sum(sxy); swh = warp_sum(swh); sob = warp_sum(sob); snb = warp_sum(snb); scl = warp_sum(scl);
+    if (lane == 0) {
+        red[warp][0] = sxy; red[warp][1] = swh; red[warp][2] = sob; red[warp][3] = snb; red[warp][4] = scl;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0;
+        for (int w = 0; w < nwarp; ++w) s += red[w][threadIdx.x];
+        partials[static_cast<size_t>(blockIdx.x) * 5 + threadIdx.x] = s;
+    }
+    // stage 2: the last block (ticket) sums all partials in block-index order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(ticket, 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // thread i: term i % 5, blocks (i / 5), (i / 5) + 25, ...; then 25 sub-sums per term in index order.
+    // The loads of a thread are issued together (one L2 round trip, not one per block) and added in
+    // block order afterwards.
+    const int term = threadIdx.x % 5, slot = threadIdx.x / 5;
+    if (slot < 25) {
+        double s = 0;
+        const int nb = static_cast<int>(gridDim.x);
+        for (int b0 = slot; b0 < nb; b0 += 25 * 16) {
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int b = b0 + 25 * j;
+                v[j] = (b < nb) ? __ldcg(partials + static_cast<size_t>(b) * 5 + term) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s += v[j];
+        }
+        fin[term][slot] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double tot = 0;
+        for (int i = 0; i < 25; ++i) tot += fin[threadIdx.x][i];
+        fin[threadIdx.x][25] = tot;
+        out_terms[threadIdx.x] = static_cast<float>(tot);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                                   // loss.py:210-213
+        out_terms[5] = static_cast<float>(static_cast<double>(cfg.lc) * (fin[0][25] + fin[1][25]) + fin[2][25] +
+                                          static_cast<double>(cfg.ln) * fin[3][25] + fin[4][25]);
+        *ticket = 0u;                                                         // ready for the next launch
+    }
+}
+
 // Persistent CTAs; each walks its tiles (tile_cells consecutive cells of y_true and y_pred) through a
 // kLossStages-deep shared-memory ring filled by cp.async.bulk (TMA, one elected thread, mbarrier
 // complete_tx), so the loads of tile i+1.. overlap the arithmetic of tile i.  Tiles that are not
@@ -78,10 +232,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
     int *heavy = reinterpret_cast<int *>(full + kLossStages);           // [tile_cells] heavy cells of the current tile
     int64_t *hcell = reinterpret_cast<int64_t *>(heavy + ((cfg.tile_cells + 1) & ~1));   // [defer_cap] global cell index
     float *hdat = reinterpret_cast<float *>(hcell + cfg.defer_cap);     // [defer_cap][2 D]: y_true row | y_pred row
-    __shared__ double red[kLossThreads / 32][5];
-    __shared__ double fin[5][26];
     __shared__ int wcount[kLossThreads / 32];
-    __shared__ bool is_last;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int64_t n_tiles = (cfg.n_cells + cfg.tile_cells - 1) / cfg.tile_cells;
@@ -119,84 +270,11 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
         __syncthreads();                                                      // list complete
         for (int h = threadIdx.x; h < n_def; h += blockDim.x) {
             const float *t = hdat + h * 2 * D;
-            const float *p = t + D;
-            float *gc = kGrad ? grad + hcell[h] * D : nullptr;
-            const float obj = t[C];                                           // loss.py:162
-            const float tx = t[C + 1], ty = t[C + 2], tw = t[C + 3], th = t[C + 4];
-            int k = 0;                                                        // loss.py:126-137
-            float u = iou_ref(tx, ty, tw, th, p[C + 1], p[C + 2], p[C + 3], p[C + 4]);
-            for (int b = 1; b < B; ++b) {
-                const float *q = p + C + 5 * b;
-                const float v = iou_ref(tx, ty, tw, th, q[1], q[2], q[3], q[4]);
-                if (v > u) { u = v; k = b; }
-            }
-            const float *q = p + C + 5 * k;
-            const float c = q[0], px = q[1], py = q[2], pw = q[3], ph_ = q[4];
-            const float noobj = __fsub_rn(1.0f, obj);
-            const float z = __fsub_rn(0.0f, c);
-            snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));
-            const float dx = __fsub_rn(tx, px), dy = __fsub_rn(ty, py);
-            sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dx, dx)));    // loss.py:171
-            sxy += static_cast<double>(__fmul_rn(obj, __fmul_rn(dy, dy)));
-            const float sw = sgn(pw), sh = sgn(ph_);
-            const float rw = __fsqrt_rn(__fadd_rn(fabsf(pw), 1e-6f)), rh = __fsqrt_rn(__fadd_rn(fabsf(ph_), 1e-6f));
-            const float dw = __fsub_rn(__fsqrt_rn(tw), __fmul_rn(sw, rw));    // loss.py:176-178
-            const float dh = __fsub_rn(__fsqrt_rn(th), __fmul_rn(sh, rh));
-            swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dw, dw)));
-            swh += static_cast<double>(__fmul_rn(obj, __fmul_rn(dh, dh)));
-            const float e = __fsub_rn(u, c);
-            sob += static_cast<double>(__fmul_rn(obj, __fmul_rn(e, e)));      // loss.py:189
-            if (kGrad) {
-                float g_c = cfg.ln * 2.0f * noobj * c;
-                float g_x = 0.f, g_y = 0.f, g_w = 0.f, g_h = 0.f;
-                if (obj != 0.0f) {
-                    // IoU pieces again, with their partial derivatives
-                    const float x1n = (tx - tw) * 0.5f, x1x = (tx + tw) * 0.5f;
-                    const float y1n = (ty - th) * 0.5f, y1x = (ty + th) * 0.5f;
-                    const float x2n = (px - pw) * 0.5f, x2x = (px + pw) * 0.5f;
-                    const float y2n = (py - ph_) * 0.5f, y2x = (py + ph_) * 0.5f;
-                    const float ddx = fminf(x1x, x2x) - fmaxf(x1n, x2n);
-                    const float ddy = fminf(y1x, y2x) - fmaxf(y1n, y2n);
-                    const float cw = clip01(ddx), ch = clip01(ddy);
-                    const float inter = cw * ch;
-                    const float a1 = fabsf((x1x - x1n) * (y1x - y1n));
-                    const float w2 = x2x - x2n, h2 = y2x - y2n;
-                    const float a2 = fabsf(w2 * h2);
-                    const float dn = ((a1 + a2) - inter) + 1e-6f;
-                    const float inv = 1.0f / dn;
-                    const float du_dI = inv + inter * inv * inv;
-                    const float du_da2 = -inter * inv * inv;
-                    const float in_x = (ddx >= 0.f && ddx <= 1.f) ? 1.f : 0.f;
-                    const float in_y = (ddy >= 0.f && ddy <= 1.f) ? 1.f : 0.f;
-                    const float mx = (x2x < x1x) ? 1.f : 0.f, nx = (x2n > x1n) ? 1.f : 0.f;
-                    const float my = (y2x < y1x) ? 1.f : 0.f, ny = (y2n > y1n) ? 1.f : 0.f;
-                    const float sa = sgn(w2 * h2);
-                    const float du_dpx = du_dI * in_x * ch * 0.5f * (mx - nx);
-                    const float du_dpy = du_dI * in_y * cw * 0.5f * (my - ny);
-                    const float du_dpw = du_dI * in_x * ch * 0.5f * (mx + nx) + du_da2 * sa * h2;
-                    const float du_dph = du_dI * in_y * cw * 0.5f * (my + ny) + du_da2 * sa * w2;
-                    const float e2 = 2.0f * obj * e;
-                    g_c -= e2;
-                    g_x = -2.0f * cfg.lc * obj * dx + e2 * du_dpx;
-                    g_y = -2.0f * cfg.lc * obj * dy + e2 * du_dpy;
-                    g_w = -2.0f * cfg.lc * obj * dw * (sw * sw) / (2.0f * rw) + e2 * du_dpw;
-                    g_h = -2.0f * cfg.lc * obj * dh * (sh * sh) / (2.0f * rh) + e2 * du_dph;
-                }
-                float *gq = gc + C + 5 * k;                                   // every other box of the cell stays 0
-                gq[0] = g_c; gq[1] = g_x; gq[2] = g_y; gq[3] = g_w; gq[4] = g_h;
-            }
+            heavy_box_terms<kGrad>(t, t + D, kGrad ? grad + hcell[h] * D : nullptr, cfg, sxy, swh, sob, snb);
         }
         for (int h = warp; h < n_def; h += nwarp) {
             const float *t = hdat + h * 2 * D;
-            const float obj = t[C];
-            if (obj != 0.0f) {                                                // loss.py:206
-                float *gc = kGrad ? grad + hcell[h] * D : nullptr;
-                for (int j = lane; j < C; j += 32) {
-                    const float d = __fsub_rn(t[j], t[D + j]);
-                    scl += static_cast<double>(__fmul_rn(obj, __fmul_rn(d, d)));
-                    if (kGrad) gc[j] = -2.0f * obj * d;
-                }
-            }
+            heavy_class_term<kGrad>(t, t + D, kGrad ? grad + hcell[h] * D : nullptr, C, lane, scl);
         }
         __syncthreads();                                                      // list may be refilled
     };
@@ -288,59 +366,101 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
     }
     if (n_def > 0) flush();
 
-    // stage 1 of the deterministic reduction: lanes -> warp -> block, fixed order
-    sxy = warp_sum(sxy); swh = warp_sum(swh); sob = warp_sum(sob); snb = warp_sum(snb); scl = warp_sum(scl);
-    if (lane == 0) {
-        red[warp][0] = sxy; red[warp][1] = swh; red[warp][2] = sob; red[warp][3] = snb; red[warp][4] = scl;
-    }
-    __syncthreads();
-    if (threadIdx.x < 5) {
-        double s = 0;
-        for (int w = 0; w < nwarp; ++w) s += red[w][threadIdx.x];
-        partials[static_cast<size_t>(blockIdx.x) * 5 + threadIdx.x] = s;
-    }
-    // stage 2: the last block (ticket) sums all partials in block-index order
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(ticket, 1u);
-        is_last = (prev == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // thread i: term i % 5, blocks (i / 5), (i / 5) + 25, ...; then 25 sub-sums per term in index order.
-    // The loads of a thread are issued together (one L2 round trip, not one per block) and added in
-    // block order afterwards.
-    const int term = threadIdx.x % 5, slot = threadIdx.x / 5;
-    if (slot < 25) {
-        double s = 0;
-        const int nb = static_cast<int>(gridDim.x);
-        for (int b0 = slot; b0 < nb; b0 += 25 * 16) {
-            double v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int b = b0 + 25 * j;
-                v[j] = (b < nb) ? __ldcg(partials + static_cast<size_t>(b) * 5 + term) : 0.0;
+    block_finish(sxy, swh, sob, snb, scl, cfg, partials, ticket, out_terms);
+}
+
+// ------------------------------------------------------------------------------------------
+// Gather variant (large batches): reads only the bytes the result depends on.
+// A "light" cell (no object, all-zero true box: ~95 % of a VOC batch) is decided by y_true[C .. C+4] and owes only the
+// no-object term on the confidence of box 0, y_pred[C] - 24 of its 2 x 4D bytes, i.e. two or three 32-byte sectors out of
+// 7.5.  So the tile is not staged through shared memory at all: thread = cell, the six values come straight from global
+// memory (read-only path, all loads of a thread in flight together), and only the heavy cells (~5 %) read their full rows,
+// through L1/L2, in the same passes B and C as above.  The gradient tile is zero-filled with 128-bit stores while the
+// loads are in flight and the few non-zero entries are written on top after the barrier.  Measured: 352 us against 389 us
+// for the ring kernel on a batch of 131,072 images (6.57 TB/s of algorithmic bytes); on the 4,096-image cfg3 batch DRAM
+// still delivers all 48 MB (its fetch granularity spans the gaps) and the ring kernel keeps a small edge (22.0 vs 22.9 us).
+// ------------------------------------------------------------------------------------------
+constexpr int kGatherThreads = 256;
+
+template <bool kGrad>
+__global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
+                                                                     LossCfg cfg, float *__restrict__ grad,
+                                                                     double *__restrict__ partials, unsigned *__restrict__ ticket,
+                                                                     float *__restrict__ out_terms)
+{
+    __shared__ int heavy[kGatherThreads];
+    __shared__ int wcount[kGatherThreads / 32];
+    const int C = cfg.C, D = cfg.D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int nwarp = kGatherThreads / 32;
+    const int64_t n_tiles = (cfg.n_cells + kGatherThreads - 1) / kGatherThreads;
+    const bool gvec_ok = kGrad && (reinterpret_cast<uintptr_t>(grad) % 16 == 0);
+    const bool pair_ok = (((C | D) & 1) == 0) && (reinterpret_cast<uintptr_t>(yt) % 8 == 0);   // y_true[C..C+3] as two aligned pairs
+    double sxy = 0, swh = 0, sob = 0, snb = 0, scl = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t cell0 = tile * kGatherThreads;
+        const int cells = static_cast<int>(min(static_cast<int64_t>(kGatherThreads), cfg.n_cells - cell0));
+        const int cell = threadIdx.x;
+        const bool in = cell < cells;
+        float obj = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, b4 = 0.f, c0 = 0.f;
+        if (in) {
+            const float *t = yt + (cell0 + cell) * D + C;
+            if (pair_ok) {
+                const float2 u = __ldg(reinterpret_cast<const float2 *>(t));
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(t + 2));
+                obj = u.x; b1 = u.y; b2 = v.x; b3 = v.y;
+            } else {
+                obj = __ldg(t); b1 = __ldg(t + 1); b2 = __ldg(t + 2); b3 = __ldg(t + 3);
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s += v[j];
+            b4 = __ldg(t + 4);
+            c0 = __ldg(yp + (cell0 + cell) * D + C);
         }
-        fin[term][slot] = s;
+        // ---- gradient tile := 0 while the loads are in flight (overwritten below where it is not) ----
+        if (kGrad) {
+            float *gg = grad + cell0 * D;
+            const int nfl = cells * D;
+            if (gvec_ok && cells == kGatherThreads) {
+                float4 *g4 = reinterpret_cast<float4 *>(gg);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = threadIdx.x; i < (nfl >> 2); i += kGatherThreads) g4[i] = z;
+            } else {
+                for (int i = threadIdx.x; i < nfl; i += kGatherThreads) gg[i] = 0.f;
+            }
+        }
+        // ---- pass A: light cells, compaction of the heavy ones ----
+        const bool hv = in && ((obj != 0.0f) || (b1 != 0.0f) || (b2 != 0.0f) || (b3 != 0.0f) || (b4 != 0.0f));
+        float g_light = 0.f;
+        if (in && !hv) {
+            const float noobj = __fsub_rn(1.0f, obj);                         // loss.py:163
+            const float z = __fsub_rn(0.0f, c0);                              // responsible = box 0
+            snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));    // loss.py:197
+            g_light = cfg.ln * 2.0f * noobj * c0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hv);
+        if (lane == 0) wcount[warp] = __popc(bal);
+        __syncthreads();                                                      // also: zero fill before the stores below
+        int base = 0, n_heavy = 0;
+#pragma unroll
+        for (int w = 0; w < nwarp; ++w) {
+            const int k = wcount[w];
+            base += (w < warp) ? k : 0;
+            n_heavy += k;
+        }
+        if (hv) heavy[base + __popc(bal & ((1u << lane) - 1u))] = cell;
+        if (kGrad && in && !hv) grad[(cell0 + cell) * D + C] = g_light;
+        __syncthreads();                                                      // heavy[] complete
+        // ---- pass B: box / confidence terms of the heavy cells, thread per cell; pass C: class term, warp per cell ----
+        for (int h = threadIdx.x; h < n_heavy; h += kGatherThreads) {
+            const int64_t off = (cell0 + heavy[h]) * D;
+            heavy_box_terms<kGrad>(yt + off, yp + off, kGrad ? grad + off : nullptr, cfg, sxy, swh, sob, snb);
+        }
+        for (int h = warp; h < n_heavy; h += nwarp) {
+            const int64_t off = (cell0 + heavy[h]) * D;
+            heavy_class_term<kGrad>(yt + off, yp + off, kGrad ? grad + off : nullptr, C, lane, scl);
+        }
+        __syncthreads();                                                      // heavy[] / wcount[] are reused by the next tile
     }
-    __syncthreads();
-    if (threadIdx.x < 5) {
-        double tot = 0;
-        for (int i = 0; i < 25; ++i) tot += fin[threadIdx.x][i];
-        fin[threadIdx.x][25] = tot;
-        out_terms[threadIdx.x] = static_cast<float>(tot);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {                                                   // loss.py:210-213
-        out_terms[5] = static_cast<float>(static_cast<double>(cfg.lc) * (fin[0][25] + fin[1][25]) + fin[2][25] +
-                                          static_cast<double>(cfg.ln) * fin[3][25] + fin[4][25]);
-        *ticket = 0u;                                                         // ready for the next launch
-    }
+    block_finish(sxy, swh, sob, snb, scl, cfg, partials, ticket, out_terms);
 }
 
 // Per-device scratch of the loss: block partials + ticket.  Calls on different streams are
@@ -358,7 +478,7 @@ struct LossGeo {
     int per_sm = 0;
 };
 static LossScratch g_loss[64];
-static LossGeo g_geo[2][64];
+static LossGeo g_geo[4][64];
 static std::mutex g_loss_mu;
 
 }  // namespace yh
@@ -388,30 +508,38 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
                static_cast<size_t>(cfg.defer_cap) * (8 + 8 * cfg.D) + 64;
     };
     while (tile > 16 && smem_of(tile) > static_cast<size_t>(100) * 1024) tile >>= 1;
-    const size_t smem = smem_of(tile);
-    if (smem > 227 * 1024) {
+    const size_t smem_tma = smem_of(tile);
+    if (smem_tma > 227 * 1024) {
         set_error("loss: C + 5B = %d too large for the shared-memory tile", cfg.D);
         return YH_ERR_UNSUPPORTED;
     }
     cfg.tile_cells = tile;
-    const int64_t n_tiles = (n_cells + tile - 1) / tile;
-    auto kern = out_grad ? loss_kernel<true> : loss_kernel<false>;
+    // two kernels: the TMA ring (lowest latency on a batch of a few thousand images, 22.0 vs 22.9 us on cfg3) and the
+    // gather variant (fewer DRAM bytes, 352 vs 389 us on a batch of 131,072); YH_LOSS_GATHER = 0 / 1 forces one of them
+    const char *gv = getenv("YH_LOSS_GATHER");                     // read per call: the tests switch it
+    const int env_gather = (gv && *gv) ? atoi(gv) : -1;
+    const bool gather = env_gather >= 0 ? env_gather != 0 : n_cells >= (1 << 20);
+    const int64_t n_tiles = gather ? (n_cells + kGatherThreads - 1) / kGatherThreads : (n_cells + tile - 1) / tile;
+    auto kern = gather ? (out_grad ? loss_gather_kernel<true> : loss_gather_kernel<false>)
+                       : (out_grad ? loss_kernel<true> : loss_kernel<false>);
+    const size_t smem = gather ? 0 : smem_tma;
+    const int threads = gather ? kGatherThreads : kLossThreads;
 
     int dev = 0;
     YH_CUDA(cudaGetDevice(&dev));
     YH_REQUIRE(dev >= 0 && dev < 64, "loss: device index %d out of range", dev);
     std::lock_guard<std::mutex> lock(g_loss_mu);
     // launch geometry is cached: the attribute / occupancy queries cost more than the kernel
-    LossGeo &g = g_geo[out_grad ? 1 : 0][dev];
+    LossGeo &g = g_geo[(out_grad ? 1 : 0) + (gather ? 2 : 0)][dev];
     if (g.smem != smem || g.per_sm == 0) {
-        YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        if (smem) YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         int per_sm = 1;
-        YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLossThreads, smem));
+        YH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         g.smem = smem;
         g.per_sm = per_sm < 1 ? 1 : per_sm;
     }
     const int grid = static_cast<int>(
-        std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * std::min(g.per_sm, std::max(1, env_ctas)))));
+        std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * (gather ? g.per_sm : std::min(g.per_sm, std::max(1, env_ctas))))));
     LossScratch &sc = g_loss[dev];
     if (sc.cap_blocks < grid) {
         if (sc.partials) {
@@ -428,7 +556,7 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
         if (!sc.ev) YH_CUDA(cudaEventCreateWithFlags(&sc.ev, cudaEventDisableTiming));
     }
     if (sc.used && sc.last != st) YH_CUDA(cudaStreamWaitEvent(st, sc.ev, 0));
-    kern<<<grid, kLossThreads, smem, st>>>(y_true, y_pred, cfg, out_grad, sc.partials, sc.ticket, out_terms);
+    kern<<<grid, threads, smem, st>>>(y_true, y_pred, cfg, out_grad, sc.partials, sc.ticket, out_terms);
     YH_LAUNCH_CHECK("loss_kernel");
     YH_CUDA(cudaEventRecord(sc.ev, st));
     sc.used = true;
