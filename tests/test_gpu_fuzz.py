@@ -1,6 +1,8 @@
 """Randomised differential test (-m gpu): the fused decode+NMS entry points against the C port over random
 shapes, batch sizes, thresholds, value distributions, element types and alignments - every kernel behind
 yh_decode_nms (tile ring, cooperative team kernel, direct kernel) gets hit.  Bit-exact bar as everywhere."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -24,9 +26,10 @@ def _check(got, want, what):
 def test_decode_nms_random_shapes():
     from yolohot import utils as yu
     dev = torch.device("cuda:0")
-    rng = np.random.default_rng(20261018)
+    # YH_FUZZ_SEED / YH_FUZZ_TRIALS: longer one-off campaigns (the defaults keep the suite short)
+    rng = np.random.default_rng(int(os.environ.get("YH_FUZZ_SEED", 20261018)))
     gens = (F.synth_dense, F.synth_quantised, F.synth_sparse, F.synth_stress)
-    for trial in range(120):
+    for trial in range(int(os.environ.get("YH_FUZZ_TRIALS", 120))):
         S = int(rng.integers(1, 17))
         B = int(rng.integers(1, 5))
         C = int(rng.choice([1, 2, 3, 5, 7, 20, 21, 33, 80, 90]))

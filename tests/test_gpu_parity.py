@@ -587,3 +587,50 @@ def test_score_mode_extension(dev):
     _check_nms((ref_b, ref_c, yu.decode_nms(_cuda(p, dev), C, B, it, ct, return_index=True)[2]), cport.decode_nms(p, C, B, it, ct), "default")
     with pytest.raises(ValueError):
         yu.decode_nms(_cuda(p, dev), C, B, score_mode="prob")
+
+
+def test_concurrent_threads_and_streams(dev):
+    """Re-entrancy: four host threads, each on its own CUDA stream, run decode+NMS, the loss and
+    the mAP stages at the same time; every thread must get the single-threaded results bit for bit."""
+    import threading
+    from yolohot import loss as yl, utils as yu
+    p = _cuda(F.synth_dense(20000, seed=21), dev)
+    yt = _cuda(F.synth_labels(600, seed=21), dev)
+    yp = _cuda(F.synth_loss_pred((600, 7, 7, 30), seed=21), dev)
+    mt = F.synth_labels(300, seed=22)
+    mp_ = _cuda(F.synth_map_pred(mt), dev)
+    mt = _cuda(mt, dev)
+
+    def work():
+        b, c, k = yu.decode_nms(p, 20, 2, return_index=True)
+        terms, grad = yl.yolo_v1_loss_terms(yt, yp, grad=True)
+        ev = yu.MeanAveragePrecision(20, 2)
+        ev.update_state(mt, mp_)
+        m = ev.result()
+        msk = torch.arange(49, device=dev)[None, :] < c[:, None]
+        return (c.clone(), b[msk].clone(), k[msk].clone(), terms.clone(), grad.clone(), float(m))
+
+    want = work()
+    torch.cuda.synchronize(dev)
+    out, errs = {}, []
+
+    def run(i):
+        try:
+            s = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(s):
+                for _ in range(5):
+                    out[i] = work()
+            s.synchronize()
+        except Exception as e:                                   # surfaced below, in the main thread
+            errs.append(repr(e))
+
+    ths = [threading.Thread(target=run, args=(i,)) for i in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for i in range(4):
+        got = out[i]
+        assert all(torch.equal(g, w) for g, w in zip(got[:5], want[:5])), i
+        assert got[5] == want[5], i
