@@ -209,3 +209,12 @@ def peer_exchange(device, group=None):
                 ex = None
     _EXCHANGES[key] = ex
     return ex
+
+
+def shutdown():
+    """Collective: unmaps and frees the exchange buffers of every cached PeerExchange.  Call before
+    torch.distributed.destroy_process_group() when the process goes on to create another group."""
+    for ex in list(_EXCHANGES.values()):
+        if ex is not None:
+            ex.close()
+    _EXCHANGES.clear()

@@ -93,6 +93,9 @@ def main():
     if rank == 0:
         print(f"multigpu_check ok: world={world} mAP sharded={m_sharded:.9f} single={m_single:.9f} "
               f"exchange={'peer stores (CUDA IPC) == NCCL all-gather' if p2p else 'NCCL all-gather'} records={k_n.shape[0]}")
+    yd.shutdown()                                               # unmap / free the IPC exchange buffers (collective)
+    assert yd.peer_exchange(dev) is not None or os.environ.get("YH_DIST_P2P", "1") == "0"   # and they can be set up again
+    yd.shutdown()
     dist.destroy_process_group()
 
 
