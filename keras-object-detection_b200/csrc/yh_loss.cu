@@ -370,15 +370,17 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
 }
 
 // ------------------------------------------------------------------------------------------
-// Gather variant (large batches): reads only the bytes the result depends on.
+// Gather variant (large batches): no staging.
 // A "light" cell (no object, all-zero true box: ~95 % of a VOC batch) is decided by y_true[C .. C+4] and owes only the
-// no-object term on the confidence of box 0, y_pred[C] - 24 of its 2 x 4D bytes, i.e. two or three 32-byte sectors out of
-// 7.5.  So the tile is not staged through shared memory at all: thread = cell, the six values come straight from global
-// memory (read-only path, all loads of a thread in flight together), and only the heavy cells (~5 %) read their full rows,
-// through L1/L2, in the same passes B and C as above.  The gradient tile is zero-filled with 128-bit stores while the
-// loads are in flight and the few non-zero entries are written on top after the barrier.  Measured: 352 us against 389 us
-// for the ring kernel on a batch of 131,072 images (6.57 TB/s of algorithmic bytes); on the 4,096-image cfg3 batch DRAM
-// still delivers all 48 MB (its fetch granularity spans the gaps) and the ring kernel keeps a small edge (22.0 vs 22.9 us).
+// no-object term on the confidence of box 0, y_pred[C].  So the tile is not staged through shared memory at all:
+// thread = cell, the six values come straight from global memory (read-only path, all loads of a thread in flight
+// together), and only the heavy cells (~5 %) read their full rows, through L1/L2, in the same passes B and C as above.
+// The gradient tile is zero-filled with 128-bit stores while the loads are in flight and the few non-zero entries are
+// written on top after the barrier.  DRAM traffic is NOT reduced - ncu shows the same bytes read as the ring kernel
+// (1.54 GB at batch 131,072: the memory system fetches the sectors between the 24 needed bytes of each 120-byte cell
+// anyway, whatever cudaLimitMaxL2FetchGranularity says) - but the kernel issues half the instructions (no ring, no
+// deferral list, one barrier pair per 256 cells) at twice the occupancy: 350 us against 376 us for the ring kernel at
+// batch 131,072 (DRAM at 6.6 TB/s).  On the 4,096-image cfg3 batch the ring kernel keeps a small edge (22.0 vs 22.9 us).
 // ------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
 
@@ -515,7 +517,7 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
     }
     cfg.tile_cells = tile;
     // two kernels: the TMA ring (lowest latency on a batch of a few thousand images, 22.0 vs 22.9 us on cfg3) and the
-    // gather variant (fewer DRAM bytes, 352 vs 389 us on a batch of 131,072); YH_LOSS_GATHER = 0 / 1 forces one of them
+    // gather variant (half the instructions, 352 vs 389 us on a batch of 131,072); YH_LOSS_GATHER = 0 / 1 forces one of them
     const char *gv = getenv("YH_LOSS_GATHER");                     // read per call: the tests switch it
     const int env_gather = (gv && *gv) ? atoi(gv) : -1;
     const bool gather = env_gather >= 0 ? env_gather != 0 : n_cells >= (1 << 20);
