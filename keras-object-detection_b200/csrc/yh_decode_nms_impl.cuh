@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -435,6 +436,38 @@ __device__ __forceinline__ float2 ldf2(const __nv_bfloat16 *p, int i)
     return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 
+// Packed 16-bit pairs: the class argmax of a half-precision head is taken on the packed values themselves
+// (ordering and equality of fp16 / bf16 values are those of their exact float32 widenings), so the class scores
+// are never unpacked: HMNMX2 tree, then one two-predicate packed compare per pair.
+template <typename E> struct Pair16;
+template <> struct Pair16<__half> {
+    using T2 = __half2;
+    static __device__ __forceinline__ float2 widen(T2 v) { return __half22float2(v); }
+    static __device__ __forceinline__ T2 bcast_max(T2 m) { const __half b = __hmax(__low2half(m), __high2half(m)); return __halves2half2(b, b); }
+    static __device__ __forceinline__ float lo(T2 v) { return __low2float(v); }
+    // cls = 2i+1 if the high element equals, then 2i if the low one does (lowest index wins)
+    static __device__ __forceinline__ void pick(int &cls, T2 v, T2 best, int i)
+    {
+        asm("{\n\t.reg .pred p, q;\n\tsetp.eq.f16x2 p|q, %1, %2;\n\t@q mov.s32 %0, %3;\n\t@p mov.s32 %0, %4;\n\t}"
+            : "+r"(cls) : "r"(*reinterpret_cast<const unsigned *>(&v)), "r"(*reinterpret_cast<const unsigned *>(&best)), "r"(2 * i + 1), "r"(2 * i));
+    }
+};
+template <> struct Pair16<__nv_bfloat16> {
+    using T2 = __nv_bfloat162;
+    static __device__ __forceinline__ float2 widen(T2 v)
+    {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(&v);
+        return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    }
+    static __device__ __forceinline__ T2 bcast_max(T2 m) { const __nv_bfloat16 b = __hmax(__low2bfloat16(m), __high2bfloat16(m)); return __halves2bfloat162(b, b); }
+    static __device__ __forceinline__ float lo(T2 v) { return __low2float(v); }
+    static __device__ __forceinline__ void pick(int &cls, T2 v, T2 best, int i)
+    {
+        asm("{\n\t.reg .pred p, q;\n\tsetp.eq.bf16x2 p|q, %1, %2;\n\t@q mov.s32 %0, %3;\n\t@p mov.s32 %0, %4;\n\t}"
+            : "+r"(cls) : "r"(*reinterpret_cast<const unsigned *>(&v)), "r"(*reinterpret_cast<const unsigned *>(&best)), "r"(2 * i + 1), "r"(2 * i));
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // Phase A: decode one cell (utils.py:173-208).  p may point to shared or global memory.
 // ------------------------------------------------------------------------------------------
@@ -444,7 +477,39 @@ __device__ __forceinline__ void decode_cell(const E *__restrict__ p, const NmsCf
 {
     float bx, by, bw, bh;
     float cbest;                                                   // the winning class score (score_mode 1 only)
-    if constexpr (CT > 0 && BT > 0 && ((CT + 5 * BT) % 2 == 0)) {
+    if constexpr (CT > 0 && BT > 0 && ((CT + 5 * BT) % 2 == 0) && (CT % 2 == 0) && !std::is_same<E, float>::value) {
+        // half-precision head: class argmax on the packed pairs, only the box values are widened
+        using P = Pair16<E>;
+        using T2 = typename P::T2;
+        constexpr int D = CT + 5 * BT;
+        const T2 *p2 = reinterpret_cast<const T2 *>(p);
+        T2 w[D / 2];
+#pragma unroll
+        for (int i = 0; i < D / 2; ++i) w[i] = p2[i];
+        T2 m = w[0];
+#pragma unroll
+        for (int i = 1; i < CT / 2; ++i) m = __hmax2(m, w[i]);
+        const T2 bb = P::bcast_max(m);
+        cls = CT - 1;
+#pragma unroll
+        for (int i = CT / 2 - 1; i >= 0; --i) P::pick(cls, w[i], bb, i);
+        cbest = P::lo(bb);
+        float v[5 * BT];
+#pragma unroll
+        for (int i = 0; i < (5 * BT) / 2; ++i) {
+            const float2 x = P::widen(w[CT / 2 + i]);
+            v[2 * i] = x.x;
+            v[2 * i + 1] = x.y;
+        }
+        conf = v[0]; bx = v[1]; by = v[2]; bw = v[3]; bh = v[4];
+#pragma unroll
+        for (int b = 1; b < BT; ++b) {
+            if (v[5 * b] > conf) {                                 // first max over boxes (utils.py:183)
+                conf = v[5 * b]; bx = v[5 * b + 1]; by = v[5 * b + 2];
+                bw = v[5 * b + 3]; bh = v[5 * b + 4];
+            }
+        }
+    } else if constexpr (CT > 0 && BT > 0 && ((CT + 5 * BT) % 2 == 0)) {
         constexpr int D = CT + 5 * BT;
         float v[D];
 #pragma unroll

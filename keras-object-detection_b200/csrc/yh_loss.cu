@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
                                                             float *__restrict__ out_terms)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int C = cfg.C, B = cfg.B, D = cfg.D;
+    const int C = cfg.C, D = cfg.D;
     const int tile_fl = cfg.tile_cells * D;
     const uint32_t tile_bytes = static_cast<uint32_t>(tile_fl) * 4u;
     float *ring = reinterpret_cast<float *>(smem);                     // [stage][0: y_true tile | 1: y_pred tile]
