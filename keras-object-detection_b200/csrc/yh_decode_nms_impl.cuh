@@ -763,6 +763,9 @@ constexpr int kTeamWarpsMax = 8;
 struct CoopCfg {
     int ST, NTEAM, TW;      // ring stages, teams per CTA, warps per team (= chunks per image)
     uint32_t chunk_bytes, last_bytes;
+    uint32_t slot_bytes;    // ring slot: chunk_bytes, + 16 when chunks may start off a 16-byte boundary
+    int shifted;            // images are not a multiple of 16 bytes: each chunk is copied as the 16-byte aligned range
+                            // around it and read at its offset a = address & 15 inside the slot
     int team_bytes;         // shared memory per team
     int64_t n;
 };
@@ -793,7 +796,7 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const E *__res
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *ring = smem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(cc.ST) * cc.chunk_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(cc.ST) * cc.slot_bytes);
     uint64_t *empty = full + cc.ST;
     volatile int64_t *issued = reinterpret_cast<volatile int64_t *>(empty + cc.ST);
     unsigned char *teams = reinterpret_cast<unsigned char *>(const_cast<int64_t *>(issued) + 2);
@@ -822,10 +825,11 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const E *__res
             for (int64_t c = 0; c < n_chunks; ++c) {
                 mbar_wait_relaxed(empty + s, ph ^ 1u, 64);
                 const uint32_t bytes = (t == cc.TW - 1) ? cc.last_bytes : cc.chunk_bytes;
-                mbar_arrive_expect_tx(full + s, bytes);
-                bulk_g2s(ring + static_cast<size_t>(s) * cc.chunk_bytes,
-                         src + (blockIdx.x + i * gridDim.x) * img_bytes + static_cast<size_t>(t) * cc.chunk_bytes, bytes,
-                         full + s, pol);
+                const int64_t off = (blockIdx.x + i * gridDim.x) * img_bytes + static_cast<int64_t>(t) * cc.chunk_bytes;
+                const uint32_t a = cc.shifted ? static_cast<uint32_t>(off & 15) : 0u;     // pred itself is 16-byte aligned
+                const uint32_t cp = (bytes + a + 15u) & ~15u;
+                mbar_arrive_expect_tx(full + s, cp);
+                bulk_g2s(ring + static_cast<size_t>(s) * cc.slot_bytes, src + off - a, cp, full + s, pol);
                 __threadfence_block();
                 *issued = c + 1;
                 if (++s == cc.ST) { s = 0; ph ^= 1u; }
@@ -870,9 +874,11 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const E *__res
         int cls = 0;
         float conf = -INFINITY;
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid)
-            decode_cell<CT, BT>(reinterpret_cast<const E *>(ring + static_cast<size_t>(s) * cc.chunk_bytes) + lane * cfg.D, cfg,
+        if (valid) {
+            const uint32_t a = cc.shifted ? static_cast<uint32_t>((img * img_bytes + static_cast<int64_t>(wt) * cc.chunk_bytes) & 15) : 0u;
+            decode_cell<CT, BT>(reinterpret_cast<const E *>(ring + static_cast<size_t>(s) * cc.slot_bytes + a) + lane * cfg.D, cfg,
                                 colf, rowf, cls, conf, box);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
         // ---- A': compaction (utils.py:95, strict >)
@@ -1113,37 +1119,45 @@ static int launch_direct(const E *pred, int64_t n, NmsCfg cfg, float *out_boxes,
 // Big images, cooperative variant (decode_nms_coop_kernel): teams of ceil(M/32) warps per image.
 template <int CT, int BT, typename E>
 static int launch_coop(const E *pred, int64_t n, NmsCfg cfg, float *out_boxes, int *out_count, int *out_idx,
-                       cudaStream_t st, bool *launched)
+                       cudaStream_t st, int64_t *done)
 {
-    *launched = false;
+    *done = 0;
     const int64_t img_bytes = static_cast<int64_t>(sizeof(E)) * cfg.M * cfg.D;
-    if (env_int("YH_COOP", 1) == 0 || reinterpret_cast<uintptr_t>(pred) % 16 != 0 || img_bytes % 16 != 0) return YH_OK;
+    if (env_int("YH_COOP", 1) == 0 || reinterpret_cast<uintptr_t>(pred) % 16 != 0 || img_bytes % 4 != 0) return YH_OK;
     CoopCfg cc;
     cc.TW = (cfg.M + 31) / 32;
     if (cc.TW > kTeamWarpsMax) return YH_OK;
     cc.chunk_bytes = 32u * cfg.D * static_cast<uint32_t>(sizeof(E));
     cc.last_bytes = static_cast<uint32_t>(img_bytes - static_cast<int64_t>(cc.TW - 1) * cc.chunk_bytes);
-    if (cc.chunk_bytes % 16 != 0 || cc.last_bytes % 16 != 0) return YH_OK;
+    if (cc.chunk_bytes % 16 != 0) return YH_OK;
+    // Images that are not a multiple of 16 bytes (odd cell / channel counts, 16-bit heads): bulk copies need 16-byte
+    // aligned ranges, so each chunk is fetched as the aligned range around it (at most 15 bytes of its neighbours on
+    // either side, all inside the tensor) and read at its offset inside a slot that is 16 bytes longer.  Only the very
+    // last chunk of the tensor could reach past its end: if that end is unaligned, the last image is left to the caller.
+    cc.shifted = (img_bytes % 16 != 0) ? 1 : 0;
+    cc.slot_bytes = cc.chunk_bytes + (cc.shifted ? 16u : 0u);
+    const int64_t n_coop = (cc.shifted && (n * img_bytes) % 16 != 0) ? n - 1 : n;
+    if (n_coop < 1 || (cc.shifted && env_int("YH_COOP_SHIFTED", 1) == 0)) return YH_OK;
     const int MPT = cc.TW * 32;
     cc.team_bytes = (MPT * 16 + MPT * 4 + MPT * 4 + (MPT + 4) * 4 + MPT * 4 + 2 * kTeamWarpsMax * 4 + MPT * (kTeamWarpsMax / 2) * 4 +
                      cfg.C * cc.TW * 4 + 15) & ~15;
     cc.NTEAM = std::max(1, std::min(std::min(15, 31 / cc.TW), env_int("YH_COOP_TEAMS", 4)));
     cc.ST = std::max(2, std::min(32, env_int("YH_COOP_STAGES", 10)));
     auto need = [&](int teams, int stg) {
-        return static_cast<size_t>(stg) * cc.chunk_bytes + 2 * static_cast<size_t>(stg) * 8 + 16 + static_cast<size_t>(teams) * cc.team_bytes + 128;
+        return static_cast<size_t>(stg) * cc.slot_bytes + 2 * static_cast<size_t>(stg) * 8 + 16 + static_cast<size_t>(teams) * cc.team_bytes + 128;
     };
     while (cc.ST > 4 && need(cc.NTEAM, cc.ST) > 227 * 1024) --cc.ST;
     while (cc.NTEAM > 1 && need(cc.NTEAM, cc.ST) > 227 * 1024) --cc.NTEAM;
     while (cc.ST > 2 && need(cc.NTEAM, cc.ST) > 227 * 1024) --cc.ST;
     if (need(cc.NTEAM, cc.ST) > 227 * 1024) return YH_OK;
-    cc.n = n;
+    cc.n = n_coop;
     const size_t smem = need(cc.NTEAM, cc.ST);
     auto kern = decode_nms_coop_kernel<CT, BT, E>;
     YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const int grid = static_cast<int>(std::min<int64_t>(n, sm_count()));
+    const int grid = static_cast<int>(std::min<int64_t>(n_coop, sm_count()));
     kern<<<grid, 32 * (1 + cc.NTEAM * cc.TW), smem, st>>>(pred, cfg, cc, out_boxes, out_count, out_idx);
     YH_LAUNCH_CHECK("decode_nms_coop_kernel");
-    *launched = true;
+    *done = n_coop;
     return YH_OK;
 }
 
@@ -1198,10 +1212,8 @@ static int launch_fused(const E *pred, int64_t n, NmsCfg cfg, float *out_boxes, 
     }
     // ---- images too large for the tile ring: cooperative team kernel ----
     if (done == 0 && (img_bytes > 12 * 1024 || img_bytes > coop_min)) {
-        bool launched = false;
-        const int rc = launch_coop<CT, BT, E>(pred, n, cfg, out_boxes, out_count, out_idx, st, &launched);
+        const int rc = launch_coop<CT, BT, E>(pred, n, cfg, out_boxes, out_count, out_idx, st, &done);
         if (rc != YH_OK) return rc;
-        if (launched) return YH_OK;
     }
     // ---- tail / fallback ----
     if (done < n) {

@@ -634,3 +634,25 @@ def test_concurrent_threads_and_streams(dev):
         got = out[i]
         assert all(torch.equal(g, w) for g, w in zip(got[:5], want[:5])), i
         assert got[5] == want[5], i
+
+
+def test_images_not_a_multiple_of_16_bytes(dev, monkeypatch):
+    """Team kernel on images whose byte size is 4, 8 or 12 mod 16 (odd cell / channel counts, 16-bit heads): chunks are
+    fetched as the aligned range around them.  Odd and even batch sizes (the last image goes to the direct kernel when the
+    tensor ends off a 16-byte boundary), against the C port and against the direct kernel."""
+    from yolohot import utils as yu
+    cases = [(7, 3, 80, torch.float32), (13, 3, 80, torch.float32), (14, 3, 80, torch.float16), (14, 3, 80, torch.bfloat16),
+             (11, 1, 20, torch.float16), (9, 2, 33, torch.float32)]
+    for S, B, C, dt in cases:
+        for n in (1, 2, 5, 300, 301):
+            p = F.synth_stress(n, S, B, C, seed=S + n, dominant=4)
+            t = torch.from_numpy(p).to(dev).to(dt)
+            img_bytes = S * S * (C + 5 * B) * t.element_size()
+            assert img_bytes % 16 != 0
+            want = cport.decode_nms(t.float().cpu().numpy(), C, B, 0.5, 0.05, nthreads=cport.num_threads())
+            got = yu.decode_nms(t, C, B, 0.5, 0.05, return_index=True)
+            _check_nms(got, want, f"shifted S={S} B={B} C={C} {dt} n={n}")
+            monkeypatch.setenv("YH_COOP_SHIFTED", "0")
+            ref = yu.decode_nms(t, C, B, 0.5, 0.05, return_index=True)
+            monkeypatch.delenv("YH_COOP_SHIFTED")
+            assert torch.equal(ref[1], got[1])
