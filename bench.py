@@ -36,6 +36,13 @@ METRIC = "post-processing images/sec (decode+IoU+NMS)"
 UNIT = "images/s"
 
 
+def base_config(world, n_img):
+    return {"workload": "cfg2: YOLOv1 S=7 B=2 C=20 decode+IoU+NMS, 1M synthetic images per GPU, dense U[0,1) seed 2025",
+            "images_per_gpu": n_img, "S": S, "B": B, "C": C, "conf_threshold": CONF_THR, "iou_threshold": IOU_THR,
+            "sharding": f"images by contiguous range x{world}, no data-path collective",
+            "l2": "inputs larger than L2 (5.88 GB read per step per GPU; no flush needed)"}
+
+
 def env_int(k, d):
     try:
         return int(os.environ.get(k, d))
@@ -125,9 +132,17 @@ def run_reference(args):
     from oracle import cport
     cport.build()
     cores = cport.num_threads()
-    n_step = env_int("YH_BENCH_REF_IMAGES", 262_144)
+    n_step = env_int("YH_BENCH_REF_IMAGES", 1_000_000)          # the stated config: 1M images per step
+    try:
+        import psutil
+        while n_step > 65_536 and n_step * (IMG_IN + M * 24 + 8) * 2 > psutil.virtual_memory().available:
+            n_step //= 2                                         # host RAM decides, and the line says so
+    except Exception:
+        pass
     rng = np.random.Generator(np.random.PCG64(2025))
-    p = rng.random((n_step, S, S, D), dtype=np.float32)
+    p = np.empty((n_step, S, S, D), dtype=np.float32)
+    for lo in range(0, n_step, 65_536):                          # generated in slices: no 2x float64 temporary
+        p[lo:lo + 65_536] = rng.random((min(65_536, n_step - lo), S, S, D), dtype=np.float32)
     for _ in range(max(1, min(args.warmup, 2))):
         cport.decode_nms(p[: n_step // 4], C, B, IOU_THR, CONF_THR, nthreads=cores, want_idx=False)
     t0 = time.perf_counter()
@@ -140,8 +155,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: YOLOv1 S=7 B=2 C=20 decode+IoU+NMS (bounded sample of the 1M-image batch)",
-                   "images_per_step": n_step, "conf_threshold": CONF_THR, "iou_threshold": IOU_THR},
+        "config": base_config(args.gpus, 1_000_000),           # the same config as the own arm ...
+        "reference_sample": {"images_per_step": n_step, "full_config": n_step == 1_000_000},   # ... and what was timed of it
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -335,6 +350,29 @@ def run_own(args):
         del h_half
     del h_in, h_boxes
 
+    # ---- sustained: >= 1,000 back-to-back launches (the K timed steps above are a burst of a few tens of ms)
+    sustained = None
+    n_sus = env_int("YH_BENCH_SUSTAINED", 1000)
+    if n_sus > 0:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_sus + 1)]
+        barrier()
+        evs[0].record(stream)
+        for k in range(n_sus):
+            step()
+            evs[k + 1].record(stream)
+        barrier()
+        ts = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(n_sus))
+        tot = evs[0].elapsed_time(evs[n_sus])
+        gbs = algo_bytes / (tot / n_sus * 1e-3) / 1e9
+        sustained = {"launches": n_sus, "seconds": tot / 1e3, "ms_mean": tot / n_sus, "ms_p50": ts[n_sus // 2],
+                     "ms_p99": ts[min(n_sus - 1, int(0.99 * n_sus))], "ms_min": ts[0], "images_per_s_per_gpu": n_img / (tot / n_sus * 1e-3),
+                     "GBps": gbs, "frac_hbm": gbs / peak}
+        if world > 1:
+            t = torch.tensor([sustained["ms_mean"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sustained["ms_mean_max_over_ranks"] = float(t[0])
+            sustained["images_per_s"] = world * n_img / (float(t[0]) * 1e-3)
+
     # ---- CPU baseline (rank 0, N=1 only): oracle C port on a bounded slice of the same inputs
     cpu_baseline = None
     extras = {}
@@ -361,8 +399,16 @@ def run_own(args):
                         "sample": f"first {n_cpu} images of the same batch x {reps} passes ({dt:.1f} s), oracle C port "
                                   f"(reference itself is TF-eager Python, not importable: no TensorFlow)",
                         "kept_counts_equal_gpu": audit, "value_1_core": one_core}
-        # ---- the other BASELINE configs, briefly (kernel time, resident inputs)
-        extras = other_configs(torch, dev, L, _lib, yu, sp)
+    del pred, boxes
+    torch.cuda.empty_cache()
+    # ---- the other BASELINE configs (kernel time, resident inputs): cfg4 (sharded when N > 1) and cfg5 at EVERY N,
+    # cfg1 / cfg2-sparse / cfg3 at N = 1
+    ctx = dict(torch=torch, dist=dist, dev=dev, L=L, _lib=_lib, yu=yu, sp=sp, rank=rank, world=world)
+    if env_int("YH_BENCH_EXTRAS", 1):
+        extras.update(cfg5_stress(ctx))
+        extras.update(cfg4_map(ctx))
+        if world == 1:
+            extras.update(other_configs(ctx))
 
     clocks = clk.summary()
     clocks["e2e"] = clk2.summary()
@@ -370,12 +416,11 @@ def run_own(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "cfg2: YOLOv1 S=7 B=2 C=20 decode+IoU+NMS, 1M synthetic images per GPU, dense U[0,1) seed 2025",
-                   "images_per_gpu": n_img, "S": S, "B": B, "C": C, "conf_threshold": CONF_THR, "iou_threshold": IOU_THR,
-                   "sharding": f"images by contiguous range x{world}, no data-path collective",
-                   "l2": "inputs larger than L2 (5.88 GB read per step per GPU; no flush needed)"},
+        "config": base_config(world, n_img),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_job, "clocks": clocks,
     }
+    if sustained is not None:
+        line["sustained"] = sustained
     line.update(extras)
     if e2e_half is not None:
         line["e2e_float16_head"] = e2e_half
@@ -386,23 +431,179 @@ def run_own(args):
     return 0
 
 
-def other_configs(torch, dev, L, _lib, yu, sp):
-    """cfg2-sparse, cfg3 (loss fwd+bwd, batch 4096) and cfg4 (mAP, 5k images) - context numbers."""
+def _timed(torch, dev, fn, reps):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    return statistics.mean(ts), min(ts)
+
+
+def _max_over_ranks(ctx, v):
+    if ctx["world"] == 1:
+        return float(v)
+    t = ctx["torch"].tensor([float(v)], device=ctx["dev"], dtype=ctx["torch"].float64)
+    ctx["dist"].all_reduce(t, op=ctx["dist"].ReduceOp.MAX)
+    return float(t[0])
+
+
+def cfg5_stress(ctx):
+    """BASELINE configs[4]: S=14 B=3 C=80, conf threshold 0.05, ~80 % of the argmaxes in 4 dominant classes,
+    131,072 images PER GPU (9.76 GB each), images sharded by range - no collective on this path."""
+    torch, dev, L, _lib, sp, world = ctx["torch"], ctx["dev"], ctx["L"], ctx["_lib"], ctx["sp"], ctx["world"]
+    peak, _ = measured_peak()
+    S5, B5, C5 = 14, 3, 80
+    n5 = env_int("YH_BENCH_CFG5_IMAGES", 131_072)
+    gen = torch.Generator(device=dev); gen.manual_seed(99 + ctx["rank"])
+    p5 = torch.rand((n5, S5, S5, C5 + 5 * B5), generator=gen, device=dev)
+    for lo in range(0, n5, 16_384):                                   # in slices: the masks are as large as a channel plane
+        v = p5[lo:lo + 16_384]
+        dom = torch.randint(0, 4, v.shape[:3], generator=gen, device=dev)
+        boost = torch.rand(v.shape[:3], generator=gen, device=dev) < 0.8
+        for k in range(4):
+            v[..., k] += 1.5 * (boost & (dom == k)).float()
+        for b in range(B5):
+            v[..., C5 + 5 * b + 3:C5 + 5 * b + 5] = 0.1 + 0.5 * v[..., C5 + 5 * b + 3:C5 + 5 * b + 5]
+        del dom, boost
+    boxes5 = torch.empty((n5, S5 * S5, 6), device=dev); cnt5 = torch.empty((n5,), device=dev, dtype=torch.int32)
+    f5 = lambda: _lib.check(L.yh_decode_nms(p5.data_ptr(), n5, S5, B5, C5, IOU_THR, 0.05, boxes5.data_ptr(), cnt5.data_ptr(), None, sp))
+    ms, mn = _timed(torch, dev, f5, 10)
+    kept5 = int(cnt5.sum().item())
+    gbs = (n5 * (4 * S5 * S5 * (C5 + 5 * B5) + 4) + 24 * kept5) / (ms * 1e-3) / 1e9
+    ms_job = _max_over_ranks(ctx, ms)
+    out = {"images_per_gpu": n5, "images_per_s": world * n5 / (ms_job * 1e-3), "ms": ms_job, "ms_rank0": ms, "ms_min_rank0": mn,
+           "GBps_per_gpu": gbs, "frac_hbm": gbs / peak, "kept_per_image": kept5 / n5, "n_gpus": world,
+           "kernel": "decode_nms_coop_kernel<80,3>"}
+    del p5, boxes5, cnt5
+    torch.cuda.empty_cache()
+    return {"cfg5_stress": out}
+
+
+def cfg4_map(ctx):
+    """BASELINE configs[3]: VOC-style mAP@0.5 over 5k synthetic images through the evaluator (update_state + result()).
+    N = 1: one GPU.  N > 1: the images are sharded by contiguous range, every rank feeds its shard to a sharded
+    evaluator; result() exchanges the records with kernels over NVLink (no NCCL call) and every rank must get the
+    single-GPU value bit for bit (checked here, on every rank, against an unsharded local evaluator)."""
+    torch, dist, dev, _lib, yu, world, rank = ctx["torch"], ctx["dist"], ctx["dev"], ctx["_lib"], ctx["yu"], ctx["world"], ctx["rank"]
+    from tests import fixtures as F
+    from yolohot import dist as yd
+    n = 5000
+    yt5 = F.synth_labels(n, seed=11); mp5 = F.synth_map_pred(yt5)
+    a_all, b_all = torch.from_numpy(yt5).to(dev), torch.from_numpy(mp5).to(dev)
+    e1 = yu.MeanAveragePrecision(C, B)
+    e1.update_state(a_all, b_all)
+    m_single = float(e1.result())
+    lo, hi = yd.shard_range(n, rank, world)
+    a, b_ = a_all[lo:hi].contiguous(), b_all[lo:hi].contiguous()
+    ev = yu.MeanAveragePrecision(C, B, sharded=world > 1)
+
+    def run_map():
+        ev.reset_states()
+        ev.update_state(a, b_)
+        return ev.result()
+    for _ in range(3):
+        m = run_map()
+    mval = float(m)
+    nrec = int(ev._st["cursors"][0].item())
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    reps = 20
+    l0 = _lib.launch_count()
+    e0, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps):
+        m = run_map()
+    e1_.record()
+    torch.cuda.synchronize(dev)
+    wall_ms = (time.perf_counter() - t0) / reps * 1e3
+    gpu_ms = e0.elapsed_time(e1_) / reps
+    launches = (_lib.launch_count() - l0) / reps
+    sync_ms = []                                                     # one pass at a time, result read on the host
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        float(run_map())
+        sync_ms.append((time.perf_counter() - t0) * 1e3)
+    out = {"images": n, "n_gpus": world, "mAP": mval, "mAP_single_gpu": m_single, "records_this_rank": nrec,
+           "ms_update_plus_result": _max_over_ranks(ctx, wall_ms), "gpu_ms_update_plus_result": _max_over_ranks(ctx, gpu_ms),
+           "ms_update_plus_result_host_read": _max_over_ranks(ctx, statistics.median(sync_ms)),
+           "kernel_launches_per_pass": launches, "host_syncs_per_pass": 0,
+           "path": "decode+NMS x2 -> yh_eval_update (append + match) -> " +
+                   ("yh_map_exchange (peer stores over NVLink) -> yh_map_reduce_exchanged" if world > 1 else "yh_map_reduce")}
+    if world > 1:
+        ok = torch.tensor([1 if mval == m_single else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        tot = torch.tensor([nrec], device=dev, dtype=torch.int64)
+        dist.all_reduce(tot)
+        ex = yd.peer_exchange(dev, C, 0)
+        rec_l, gt_l = ev._st["rec"][:nrec], ev._st["gt"]
+
+        def nccl_path():
+            r_all, g_all = yd.gather_records(rec_l, gt_l)
+            return yu.map_reduce(r_all, g_all, C)[0]
+        m_nccl = float(nccl_path())
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            nccl_path()
+        torch.cuda.synchronize(dev)
+        nccl_ms = (time.perf_counter() - t0) / reps * 1e3
+
+        def peer_path():
+            return ex.exchange_reduce(ev._st["rec"], ev._st["cursors"][0:1], gt_l, nrec)[0]
+        peer_ms = None
+        if ex is not None:
+            float(peer_path())
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                peer_path()
+            torch.cuda.synchronize(dev)
+            peer_ms = _max_over_ranks(ctx, (time.perf_counter() - t0) / reps * 1e3)
+        out.update({"equal_single_gpu": bool(int(ok[0])), "records_exchanged": int(tot[0]),
+                    "bytes_over_nvlink_per_rank": 8 * nrec * (world - 1) + 4 * C * (world - 1),
+                    "exchange": "kernel-level peer stores (CUDA IPC)" if ex is not None else "padded NCCL all-gathers",
+                    "ms_exchange_plus_reduce_peer_stores": peer_ms,
+                    "ms_exchange_plus_reduce_padded_nccl": _max_over_ranks(ctx, nccl_ms), "mAP_padded_nccl_path": m_nccl,
+                    "exchange_error_flag": ex.error() if ex is not None else None})
+        key = "cfg4_map_sharded"
+    else:
+        # the same evaluator over 1 M images: result() alone (records stay on the device)
+        key = "cfg4_map_5k_images"
+    return {key: out}
+
+
+def map_one_million(ctx):
+    """result() over the records of 1 M images (context for the reduce kernel at scale)."""
+    torch, dev, yu = ctx["torch"], ctx["dev"], ctx["yu"]
+    from tests import fixtures as F
+    yt = F.synth_labels(50_000, seed=11); mp = F.synth_map_pred(yt)
+    a, b_ = torch.from_numpy(yt).to(dev), torch.from_numpy(mp).to(dev)
+    ev = yu.MeanAveragePrecision(C, B)
+    for _ in range(20):                                               # 20 x 50k images
+        ev.update_state(a, b_)
+    ev.result()
+    ms, mn = _timed(torch, dev, ev.result, 5)
+    return {"map_1M_images": {"images": ev.img_idx, "records": int(ev._st["cursors"][0].item()), "ms_result": ms, "ms_result_min": mn}}
+
+
+def other_configs(ctx):
+    """cfg1 (batch 64), cfg2-sparse and cfg3 (loss fwd+bwd, batch 4096) - context numbers, N = 1."""
     import numpy as np
     from tests import fixtures as F
+    torch, dev, L, _lib, sp = ctx["torch"], ctx["dev"], ctx["L"], ctx["_lib"], ctx["sp"]
     out = {}
     peak, _ = measured_peak()
-
-    def timed(fn, reps):
-        for _ in range(3):
-            fn()
-        ts = []
-        for _ in range(reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            torch.cuda.synchronize(dev)
-            ts.append(a.elapsed_time(b))
-        return statistics.mean(ts), min(ts)
+    timed = lambda fn, reps: _timed(torch, dev, fn, reps)
 
     # cfg1: batch 64 (BASELINE configs[0], the reference's own CPU-runnable case): launch-bound, so also as a CUDA graph
     p64 = torch.from_numpy(F.synth_dense(64, seed=1234)).to(dev)
@@ -480,41 +681,7 @@ def other_configs(torch, dev, L, _lib, yu, sp):
                                       "l2": "8 rotating buffer sets (578 MB > L2), back-to-back launches",
                                       "device_copy_same_traffic_ms": cms, "frac_of_same_size_copy": cms / ms}
     del cs
-    # cfg5: stress S=14 B=3 C=80, conf threshold 0.05, ~80 % of the argmaxes in 4 dominant classes
-    S5, B5, C5 = 14, 3, 80
-    n5 = env_int("YH_BENCH_CFG5_IMAGES", 65_536)
-    gen = torch.Generator(device=dev); gen.manual_seed(99)
-    p5 = torch.rand((n5, S5, S5, C5 + 5 * B5), generator=gen, device=dev)
-    dom = torch.randint(0, 4, (n5, S5, S5), generator=gen, device=dev)
-    boost = torch.rand((n5, S5, S5), generator=gen, device=dev) < 0.8
-    for k in range(4):
-        p5[..., k] += 1.5 * (boost & (dom == k)).float()
-    for b in range(B5):
-        p5[..., C5 + 5 * b + 3:C5 + 5 * b + 5] = 0.1 + 0.5 * p5[..., C5 + 5 * b + 3:C5 + 5 * b + 5]
-    del dom, boost
-    boxes5 = torch.empty((n5, S5 * S5, 6), device=dev); cnt5 = torch.empty((n5,), device=dev, dtype=torch.int32)
-    f5 = lambda: _lib.check(L.yh_decode_nms(p5.data_ptr(), n5, S5, B5, C5, IOU_THR, 0.05, boxes5.data_ptr(), cnt5.data_ptr(), None, sp))
-    ms, mn = timed(f5, 10)
-    kept5 = int(cnt5.sum().item())
-    gbs = (n5 * (4 * S5 * S5 * (C5 + 5 * B5) + 4) + 24 * kept5) / (ms * 1e-3) / 1e9
-    out["cfg5_stress"] = {"images": n5, "images_per_s": n5 / (ms * 1e-3), "ms": ms, "GBps": gbs, "frac_hbm": gbs / peak,
-                          "kept_per_image": kept5 / n5, "kernel": "decode_nms_coop_kernel<80,3>"}
-    del p5, boxes5, cnt5
-    # cfg4: mAP over 5k images, single GPU (evaluator update + result)
-    yt5 = F.synth_labels(5000, seed=11); mp5 = F.synth_map_pred(yt5)
-    a, b_ = torch.from_numpy(yt5).to(dev), torch.from_numpy(mp5).to(dev)
-    def run_map():
-        e = yu.MeanAveragePrecision(C, B)
-        e.update_state(a, b_)
-        return e.result()
-    for _ in range(2):
-        m = run_map()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for _ in range(5):
-        m = run_map()
-    mval = float(m)
-    out["cfg4_map_5k_images"] = {"ms_update_plus_result": (time.perf_counter() - t0) / 5 * 1e3, "mAP": mval}
+    out.update(map_one_million(ctx))
     return out
 
 

@@ -104,12 +104,30 @@ YH_API int yh_filter_rows(const float *rows, int64_t n, int M, float conf_thr,
 
 /* ---- evaluator rows: utils.py:476-489 (prefix img_idx, append) ------------------------
  * Compacts padded NMS output (n, M, 6) + count (n) into rows [img, cls, conf, cx,cy,w,h]
- * appended at out_rows + 7 * (*row_cursor) ; image i gets img index img_base + i (as
- * float32, like the reference).  row_cursor is a DEVICE int64 counter that the call
- * advances by the number of rows written; rows beyond `out_capacity` rows are dropped and
- * the cursor still advances (the caller checks it and re-runs after growing). */
+ * appended at out_rows + 7 * (*row_cursor) in image order; image i gets img index
+ * img_base + i (as float32, like the reference).  row_cursor is a DEVICE int64 counter that
+ * the call advances by the number of rows of the batch; rows beyond `out_capacity` rows are
+ * dropped (the cursor still advances).  One kernel (single-pass chained scan), no host
+ * synchronisation.  Calls that share a stream are ordered; calls on different streams of one
+ * device may run concurrently. */
 YH_API int yh_rows_append(const float *boxes, const int32_t *count, int64_t n, int M, int64_t img_base,
                    float *out_rows, int64_t out_capacity, int64_t *row_cursor, void *stream);
+
+/* ---- evaluator update: the whole accumulation step of MeanAveragePrecision.update_state
+ * (utils.py:470-491) after decode + NMS, in ONE kernel: appends the prediction rows and the
+ * ground-truth rows of the batch like yh_rows_append (cursors[0] / cursors[1], device int64)
+ * and matches every image on the spot (utils.py:373-422): a detection can only claim a ground
+ * truth of its own image, and NMS emits an image's detections in the reference's processing
+ * order, so the TP / FP decision of a detection is final as soon as its image is seen.
+ * rec (pred_capacity) receives one packed record per prediction row, at the row's index:
+ *     uint64 = class << 33 | ~orderable(conf) << 1 | tp        (orderable: monotone float -> uint32)
+ * gt_per_class (C int32) ACCUMULATES the ground truths per class (zero it when the evaluator
+ * restarts).  result() is then yh_map_reduce over rec[0 .. cursors[0]) - no host sync anywhere. */
+YH_API int yh_eval_update(const float *pred_boxes, const int32_t *pred_count,
+                   const float *true_boxes, const int32_t *true_count,
+                   int64_t n, int M, int64_t img_base, int C, float iou_thr,
+                   float *pred_rows, int64_t pred_capacity, float *true_rows, int64_t true_capacity,
+                   uint64_t *rec, int64_t *cursors, int32_t *gt_per_class, void *stream);
 
 /* ---- loss: loss.py:120-215 YoloV1Loss.call (+ its autodiff backward) ------------------
  * y_true, y_pred: (n_cells, C+5B) i.e. the (N,S,S,D) tensors flattened over cells.
@@ -120,60 +138,79 @@ YH_API int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells, in
             float *out_terms, float *out_grad, void *stream);
 
 /* ---- mAP: utils.py:303-456 mean_average_precision -------------------------------------
- * Stage 1 (per image shard, no communication): greedy IoU matching of detections to
- * ground truths.  true_rows (nt,7), pred_rows (np,7) rows [img, cls, conf, cx,cy,w,h].
- * Writes, for the np detections in (class asc, conf desc, row asc) order:
- *   out_keys (np) uint64 = class << 32 | ~orderable(conf)   (sort key of stage 2)
- *   out_tp   (np) uint8  = 1 true positive / 0 false positive
- * and out_gt_per_class (C) int32 = number of ground truths per class.
- * Rows whose class is not an integer in [0, C) are ignored (the reference never selects
- * them, utils.py:329-330) and get key = C << 32 | 0xffffffff (they sort after every class). */
-YH_API int yh_map_match(const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
-                 int C, float iou_thr,
-                 uint64_t *out_keys, uint8_t *out_tp, int32_t *out_gt_per_class, void *stream);
+ * Stage 1 on arbitrary rows (per image shard, no communication): greedy IoU matching of
+ * detections to ground truths.  true_rows (nt,7), pred_rows (np,7) rows
+ * [img, cls, conf, cx,cy,w,h] in any order.  nt_dev / np_dev (nullable): DEVICE int64 row
+ * counts (<= nt / np, which then only bound the buffers) - e.g. an evaluator's cursors.
+ * flags: YH_MAP_TRUE_ROWS_BY_IMAGE = the ground-truth rows are grouped by image with
+ * nondecreasing image index (what an evaluator accumulates); otherwise they are first ordered
+ * by image with a stable radix sort.
+ * out_rec (np): one packed record per detection, in ROW order (layout: yh_eval_update);
+ * out_gt_per_class (C int32): ground truths per class.  Rows whose class is not an integer in
+ * [0, C) are ignored (the reference never selects them, utils.py:329-330); their record carries
+ * class C and sorts after every class.
+ * workspace: yh_workspace_bytes(YH_OP_MAP_MATCH, max(nt, np), ..) bytes, 256-byte aligned, or
+ * NULL (stream-ordered allocation inside the call). */
+#define YH_MAP_TRUE_ROWS_BY_IMAGE 1
+YH_API int yh_map_match(const float *true_rows, int64_t nt, const int64_t *nt_dev,
+                 const float *pred_rows, int64_t np, const int64_t *np_dev,
+                 int C, float iou_thr, int flags,
+                 uint64_t *out_rec, int32_t *out_gt_per_class,
+                 void *workspace, size_t workspace_bytes, void *stream);
 
-/* Stage 2 (after the shards' records were concatenated in shard order, e.g. by an NCCL
- * all-gather, and the per-class GT counts summed): stable sort by key, cumulative TP/FP,
- * precision/recall, trapezoid AP per class (out_ap (C), nullable) and their mean
- * (out_map (1)). */
-YH_API int yh_map_reduce(const uint64_t *keys, const uint8_t *tp, int64_t nrec,
-                  const int32_t *gt_per_class, int C, float *out_ap, float *out_map, void *stream);
+/* Stage 2 (on the records of all shards concatenated in shard order = image order, and the
+ * per-class ground-truth counts summed): ONE persistent cooperative kernel - stable radix sort
+ * by (class asc, confidence desc), cumulative TP / FP, precision / recall, np.trapz AP per class
+ * (out_ap (C), nullable) and the mean over all C classes (out_map (1)).  nrec_dev (nullable):
+ * DEVICE int64 record count (<= nrec, which then only bounds the buffers); n_hint: expected
+ * record count (sizes the grid only, any value is correct; 0 = nrec).  workspace:
+ * yh_workspace_bytes(YH_OP_MAP_REDUCE, nrec, ..) bytes, 256-byte aligned, or NULL.  No host
+ * synchronisation; capturable in a CUDA graph (the count is re-read at every replay). */
+YH_API int yh_map_reduce(const uint64_t *rec, int64_t nrec, const int64_t *nrec_dev, int64_t n_hint,
+                  const int32_t *gt_per_class, int C, float *out_ap, float *out_map,
+                  void *workspace, size_t workspace_bytes, void *stream);
 
-/* ---- multi-GPU exchange step of the mAP, single process driving all devices -------------
- * (the Python mirror uses one process per GPU over torch.distributed instead, with
- * the same result.)  Between yh_map_match on every shard and yh_map_reduce: the records of all
- * devices are concatenated in device order (= image order) on every device, and the per-class
- * ground-truth counts are summed.  NCCL is loaded at run time (libnccl.so.2 of the process).
- * yh_comm_init_all: ncclCommInitAll over `devs` (NULL = 0..ndev-1).
- * yh_map_allgather: keys[d] / tp[d] hold nrec[d] records on device d (nrec is a HOST array),
- * gt_per_class[d] (C int32, device d) is all-reduced in place; out_keys[d] / out_tp[d] (device d,
- * capacity out_capacity records) receive the concatenation; streams[d] (nullable) is device d's
- * stream.  Asynchronous on those streams. */
+/* ---- multi-GPU exchange step of the mAP -------------------------------------------------
+ *   Between stage 1 on every shard and stage 2.
+ *
+ * (a) Fused with kernels over peer-mapped memory (NVLink / NVSwitch), no collective call and no
+ * host synchronisation.  Every rank owns one exchange buffer of yh_map_exchange_bytes(n, C,
+ * capacity) bytes, zero-filled once, writable by all its peers: cudaDeviceEnablePeerAccess in
+ * one process (yh_comm_init_all does it), or yh_ipc_alloc / yh_ipc_open between processes.
+ * yh_map_exchange on rank `self` stores its records (rec[0 .. *nrec_dev)), their count and its
+ * per-class ground-truth counts into slot `self` of EVERY rank's buffer (bufs[0..n)), then
+ * releases a per-rank flag = epoch.  yh_map_reduce_exchanged on a rank waits (bounded, ~2 s) for
+ * the n flags of `epoch` in its own buffer and reduces the n segments in rank order.  epoch
+ * starts at 1 and increases by 1 per exchange, in lockstep on all ranks (double buffered by its
+ * parity).  capacity = records per rank and epoch the buffers were sized for (equal on all
+ * ranks).  err (nullable device int32) receives YH_MAP_ERR_TIMEOUT / YH_MAP_ERR_OVERFLOW (a
+ * rank's shard exceeded `capacity`); the result is then meaningless.  n_hint: expected total
+ * record count (sizes the grid only; 0 = n * capacity). */
+#define YH_MAP_ERR_TIMEOUT 1
+#define YH_MAP_ERR_OVERFLOW 2
+YH_API size_t yh_map_exchange_bytes(int n_peers, int C, int64_t capacity);
+YH_API int yh_map_exchange(int n_peers, int self, void *const *bufs, int C, int64_t capacity,
+                    const uint64_t *rec, int64_t nrec_max, const int64_t *nrec_dev,
+                    const int32_t *gt_per_class, uint64_t epoch, void *stream);
+YH_API int yh_map_reduce_exchanged(int n_peers, void *own_buf, int C, int64_t capacity, uint64_t epoch, int64_t n_hint,
+                            float *out_ap, float *out_map, int32_t *err,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* (b) As a collective, single process driving all devices: yh_comm_init_all = ncclCommInitAll
+ * over `devs` (NULL = 0..ndev-1; NCCL is loaded at run time from the libnccl.so.2 of the
+ * process) + peer access + one event per device.  yh_map_allgather: rec[d] holds nrec[d] records
+ * on device d (nrec is a HOST array), gt_per_class[d] (C int32, device d) is all-reduced in
+ * place; out_rec[d] (device d, capacity out_capacity records) receives the concatenation in
+ * device order; streams[d] (nullable) is device d's stream.  Asynchronous on those streams.
+ * yh_comm_p2p: 1 when every device can access every other device's memory (then (a) works on
+ * plain cudaMalloc buffers); yh_comm_barrier: cross-device barrier on the streams, no host wait. */
 YH_API int yh_comm_init_all(int ndev, const int *devs, void **comm);
 YH_API int yh_comm_destroy(void *comm);
-YH_API int yh_map_allgather(void *comm, const uint64_t *const *keys, const uint8_t *const *tp, const int64_t *nrec,
-                     int32_t *const *gt_per_class, int C, uint64_t *const *out_keys, uint8_t *const *out_tp,
+YH_API int yh_map_allgather(void *comm, const uint64_t *const *rec, const int64_t *nrec,
+                     int32_t *const *gt_per_class, int C, uint64_t *const *out_rec,
                      int64_t out_capacity, void *const *streams);
-
-/* The exchange step FUSED into stage 1 over peer-mapped memory (NVLink / NVSwitch), no collective call: device
- * `dev_index` matches its shard like yh_map_match and its last kernel stores every record (key, TP flag) at
- * [offset, offset + np) of the record buffers of ALL devices, and adds its per-class ground-truth counts into all
- * devices' accumulators gt_sum_all[d] (C int32 each, zeroed by the caller).  offset = number of detections of the
- * shards before this one (device order = image order).  Needs yh_comm_p2p(comm) == 1.  Surround the calls of all
- * devices with yh_comm_barrier: zero the accumulators, barrier, match on every device, barrier, yh_map_reduce. */
 YH_API int yh_comm_p2p(void *comm);
 YH_API int yh_comm_barrier(void *comm, void *const *streams);
-YH_API int yh_map_match_p2p(void *comm, int dev_index, const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
-                     int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
-                     int32_t *const *gt_sum_all, void *stream);
-
-/* The same fused stage for ANY set of peer-mapped buffers - e.g. one process per GPU, buffers of the other processes
- * mapped through CUDA IPC (yh_ipc_*): this device is peer `self` of `n_peers`.  gt_sum_all may be NULL (no system
- * atomics; the shard's own counts go to out_gt_local and the caller sums them, e.g. with the all-reduce that also
- * orders the peers' stores before the reduce stage); out_gt_local may be NULL when gt_sum_all is given. */
-YH_API int yh_map_match_peers(int n_peers, int self, const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
-                       int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
-                       int32_t *const *gt_sum_all, int32_t *out_gt_local, void *stream);
 
 /* Device buffers that other processes of the same box can map: yh_ipc_alloc = cudaMalloc (zero-filled) + an opaque
  * YH_IPC_HANDLE_BYTES handle to send to the peers; yh_ipc_open maps a peer's handle (never one's own) with peer access
@@ -184,7 +221,8 @@ YH_API int yh_ipc_open(const unsigned char *handle, void **ptr);
 YH_API int yh_ipc_close(void *ptr);
 YH_API int yh_ipc_free(void *ptr);
 
-/* Device scratch (bytes) an operation allocates internally for n images / rows; informational. */
+/* Device scratch (bytes) of an operation for n images / rows.  The mAP stages take it as a caller
+ * workspace (or allocate it themselves when passed NULL); the others allocate internally. */
 #define YH_OP_DECODE_NMS 1
 #define YH_OP_DECODE_NMS_HOST 2
 #define YH_OP_LOSS 3

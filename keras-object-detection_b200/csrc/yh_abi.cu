@@ -83,7 +83,7 @@ static int view_of(const DLManagedTensor *m, const char *name, uint8_t code, uin
 
 using namespace yh;
 
-extern "C" int yh_version(void) { return 1000 * 0 + 1; }
+extern "C" int yh_version(void) { return 1000 * 0 + 2; }
 
 extern "C" const char *yh_last_error(void) { return g_err; }
 

@@ -44,6 +44,45 @@ struct Comm {
     bool p2p = false;       // every device can read/write every other device's memory (NVLink / NVSwitch)
 };
 
+// ---- mAP records (yh_map.cu, yh_map_reduce.cu, yh_comm.cu) ------------------------------------
+// One detection = one uint64:  class << 33 | ~orderable(conf) << 1 | tp.  Ascending order of the bits above
+// bit 0 is (class asc, confidence desc) - the reference's processing order, utils.py:367; a stable sort on
+// those bits keeps the row order among equal confidences.  Rows whose class is not an integer in [0, C)
+// carry class = C (the reference never selects them, utils.py:329-330) and sort after every class.
+constexpr int kRecClassShift = 33;
+constexpr int kMaxMapClasses = 4096;          // shared-memory tables of the mAP kernels
+constexpr int kMaxSegs = kMaxPeers;           // record segments (one per rank) the reduce stage takes
+
+__host__ __device__ inline int class_bits(int C)
+{
+    int b = 1;
+    while ((1ll << b) <= C) ++b;
+    return b;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t orderable(float f)
+{
+    f = __fadd_rn(f, 0.0f);                       // -0 -> +0 so that equal floats get equal keys
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// class of a row as an integer in [0, C), or C when the reference would never select the row
+// (utils.py:329-330 compare the float class with float(c), c = 0..C-1)
+__device__ __forceinline__ uint32_t class_of(float cf, int C)
+{
+    const int ci = static_cast<int>(cf);
+    return (cf >= 0.0f && cf < static_cast<float>(C) && static_cast<float>(ci) == cf) ? static_cast<uint32_t>(ci)
+                                                                                    : static_cast<uint32_t>(C);
+}
+
+__device__ __forceinline__ uint64_t make_rec(uint32_t cls, float conf, uint32_t tp)
+{
+    return (static_cast<uint64_t>(cls) << kRecClassShift) | (static_cast<uint64_t>(~orderable(conf)) << 1) | tp;
+}
+#endif
+
 inline int sm_count()
 {
     static int cached[64] = {0};

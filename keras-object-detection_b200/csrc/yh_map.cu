@@ -1,262 +1,33 @@
-// yh_map.cu - K6/K7: IoU matching behind mAP and the per-class AP reduction, plus the
-// evaluator's row compaction.  sm_100a.
+// yh_map.cu - K6: the evaluator's accumulation step and the IoU matching behind mAP.  sm_100a, hand-written
+// (no CUB): one kernel per update, no host synchronisation anywhere.
 //
-// Replaces utils.py:303-456 (mean_average_precision, change_tensor :280-299) and the append
-// of MeanAveragePrecision.update_state utils.py:476-489.
+// Replaces MeanAveragePrecision.update_state (utils.py:470-491: prefix img_idx, append) and the matching loop
+// of mean_average_precision (utils.py:373-422, change_tensor :280-299).
 //
-// The reference walks, per class, the detections in stable descending-confidence order and
-// lets each one claim the ground truth of its image with the highest IoU (strict >, first
-// wins) if that IoU is > thr and the GT is still free (utils.py:373-422).  Which GT a
-// detection points at does not depend on the claims, so:
-//   K6a  ground truths are grouped by (class, image) with a stable radix sort (row order kept
-//        inside a group = the reference's `ground_truth_img` order, utils.py:378)
-//   K6b  detections are put in (class asc, conf desc, row asc) order - the reference's
-//        processing order, utils.py:367 - by one stable radix sort
-//   K6c  one thread per detection: binary search of its (class, image) GT group, best IoU;
-//        hits do atomicMin(claim[gt], sorted position): the earliest detection owns the GT
-//   K6d  TP <=> the detection owns the GT it points at
-//   K7   (after shards are concatenated) stable sort by (class, ~conf), inclusive scan of
-//        TP, float32 precision/recall points exactly as utils.py:430-439, trapezoid terms as
-//        np.trapz on float32, summed per class in float64 by one CTA in a fixed order.
-// Radix sort / scan are CUB device primitives (library calls, like cuBLAS would be).
-#include <cub/cub.cuh>
-
-#include <algorithm>
+//   eval_update_kernel   one launch per update_state: a single-pass chained scan (decoupled look-back over the
+//                        CTAs' tile totals) turns the kept-row counts of the batch into global row offsets; one
+//                        warp per image appends its rows [img, cls, conf, cx, cy, w, h] to the prediction and
+//                        ground-truth row buffers in image order and - because a detection can only ever claim a
+//                        ground truth of its own image, and NMS already emits an image's detections in the
+//                        reference's processing order (confidence descending, stable) - matches the image right
+//                        there: best same-class IoU (strict >, first wins, utils.py:386-393), TP iff that IoU is
+//                        > thr and the ground truth is still free (utils.py:395-418).  Out comes one packed record
+//                        per detection (yh_common.cuh) and the per-class ground-truth counts; result() is then
+//                        only the reduce stage (yh_map_reduce.cu).
+//   general path         mean_average_precision() on arbitrary rows: prep (claim table, per-class GT counts,
+//                        optionally image keys for a radix sort when the ground-truth rows are not grouped by
+//                        image) -> one thread per detection: binary search of its image's ground truths, best IoU,
+//                        atomicMin of (confidence desc, row asc) into the claim of that ground truth -> TP iff the
+//                        detection owns the ground truth it points at: the sequential claim loop without sequencing.
+#include <map>
+#include <mutex>
 
 #include "yh_common.cuh"
+#include "yh_map_internal.cuh"
 
 namespace yh {
 
-__device__ __forceinline__ uint32_t orderable(float f)
-{
-    f = __fadd_rn(f, 0.0f);                       // -0 -> +0 so that equal floats get equal keys
-    const uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-// class of a row as an integer in [0, C), or C when the reference would never select the row
-// (utils.py:329-330 compare the float class with float(c), c = 0..C-1)
-__device__ __forceinline__ uint32_t class_of(float cf, int C)
-{
-    const int ci = static_cast<int>(cf);
-    return (cf >= 0.0f && cf < static_cast<float>(C) && static_cast<float>(ci) == cf) ? static_cast<uint32_t>(ci)
-                                                                                    : static_cast<uint32_t>(C);
-}
-
-__global__ void gt_keys_kernel(const float *__restrict__ rows, int64_t n, int C, uint64_t *__restrict__ keys,
-                               uint32_t *__restrict__ vals, int *__restrict__ gt_per_class)
-{
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t c = class_of(rows[7 * i + 1], C);
-    keys[i] = (static_cast<uint64_t>(c) << 32) | orderable(rows[7 * i]);
-    vals[i] = static_cast<uint32_t>(i);
-    if (c < static_cast<uint32_t>(C)) atomicAdd(gt_per_class + c, 1);
-}
-
-__global__ void det_keys_kernel(const float *__restrict__ rows, int64_t n, int C, uint64_t *__restrict__ keys,
-                                uint32_t *__restrict__ vals)
-{
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t c = class_of(rows[7 * i + 1], C);
-    const uint32_t k = (c < static_cast<uint32_t>(C)) ? ~orderable(rows[7 * i + 2]) : 0xffffffffu;
-    keys[i] = (static_cast<uint64_t>(c) << 32) | k;
-    vals[i] = static_cast<uint32_t>(i);
-}
-
-__device__ __forceinline__ int64_t lower_bound_u64(const uint64_t *a, int64_t n, uint64_t key)
-{
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (a[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// K6c: s = sorted detection position
-__global__ void match_kernel(const float *__restrict__ pred_rows, const uint32_t *__restrict__ det_vals,
-                             const uint64_t *__restrict__ det_keys, int64_t np, const float *__restrict__ true_rows,
-                             const uint64_t *__restrict__ gt_keys, const uint32_t *__restrict__ gt_vals, int64_t nt, int C,
-                             float iou_thr, int32_t *__restrict__ hit, uint32_t *__restrict__ claim)
-{
-    const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (s >= np) return;
-    int32_t h = -1;
-    const uint32_t c = static_cast<uint32_t>(det_keys[s] >> 32);
-    if (c < static_cast<uint32_t>(C)) {
-        const float *d = pred_rows + 7ll * det_vals[s];
-        const uint64_t gk = (static_cast<uint64_t>(c) << 32) | orderable(d[0]);
-        const int64_t lo = lower_bound_u64(gt_keys, nt, gk);
-        const float dx = d[3], dy = d[4], dw = d[5], dh = d[6];
-        float best = 0.0f;                               // utils.py:382 (unwritten slot reads 0)
-        int64_t bj = lo;                                 // utils.py:383 (index defaults to 0)
-        int64_t g = lo;
-        for (; g < nt && gt_keys[g] == gk; ++g) {        // utils.py:386
-            const float *t = true_rows + 7ll * gt_vals[g];
-            const float v = iou_ref(dx, dy, dw, dh, t[3], t[4], t[5], t[6]);   // utils.py:387 (det, gt)
-            if (v > best) { best = v; bj = g; }          // utils.py:389
-        }
-        if (g > lo && best > iou_thr) {                  // utils.py:395
-            h = static_cast<int32_t>(bj);
-            atomicMin(claim + bj, static_cast<uint32_t>(s));
-        }
-    }
-    hit[s] = h;
-}
-
-// K6d
-__global__ void tp_kernel(const int32_t *__restrict__ hit, const uint32_t *__restrict__ claim, int64_t np,
-                          uint8_t *__restrict__ tp)
-{
-    const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (s >= np) return;
-    const int32_t h = hit[s];
-    tp[s] = (h >= 0 && claim[h] == static_cast<uint32_t>(s)) ? 1 : 0;   // utils.py:408-418
-}
-
-// K6d', fused with the exchange step: the TP decision of a detection and its sort key are stored straight into the
-// record buffers of EVERY device of the box (peer-mapped memory over NVLink / NVSwitch) at this shard's offset, so
-// no separate all-gather runs afterwards.  The sorted keys already sit in the local buffer (the radix sort wrote them).
-struct PeerSet {
-    int n, self;
-    uint64_t *keys[kMaxPeers];
-    uint8_t *tp[kMaxPeers];
-    int32_t *gt[kMaxPeers];
-    int64_t offset;
-    int has_gt;
-};
-
-__global__ void tp_scatter_kernel(const int32_t *__restrict__ hit, const uint32_t *__restrict__ claim, int64_t np, PeerSet ps)
-{
-    const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (s >= np) return;
-    const int32_t h = hit[s];
-    const uint8_t tp = (h >= 0 && claim[h] == static_cast<uint32_t>(s)) ? 1 : 0;   // utils.py:408-418
-    const uint64_t key = ps.keys[ps.self][ps.offset + s];
-    for (int d = 0; d < ps.n; ++d) {
-        ps.tp[d][ps.offset + s] = tp;
-        if (d != ps.self) ps.keys[d][ps.offset + s] = key;
-    }
-}
-
-// per-class ground-truth counts of this shard added into every device's accumulator (system-scope atomics)
-__global__ void gt_scatter_kernel(const int32_t *__restrict__ gt_local, int C, PeerSet ps)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const int v = gt_local[c];
-    if (v == 0) return;
-    for (int d = 0; d < ps.n; ++d) atomicAdd_system(ps.gt[d] + c, v);
-}
-
-// K7: class segment starts in the sorted record keys: start[c] = lower_bound(c << 32), c = 0..C
-__global__ void class_starts_kernel(const uint64_t *__restrict__ keys, int64_t n, int C, int64_t *__restrict__ start)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > C) return;
-    start[c] = lower_bound_u64(keys, n, static_cast<uint64_t>(c) << 32);
-}
-
-struct U8ToI32 {
-    __host__ __device__ int operator()(uint8_t v) const { return static_cast<int>(v); }
-};
-
-// precision / recall point of sorted record i of a class starting at s0 (utils.py:430-435)
-__device__ __forceinline__ void pr_point(const int *__restrict__ cum, int64_t i, int64_t s0, int base, float total,
-                                         float &rec, float &prec)
-{
-    const int tpi = cum[i] - base;
-    const float tpc = static_cast<float>(tpi);
-    const float fpc = static_cast<float>(static_cast<int>(i - s0 + 1) - tpi);
-    rec = __fdiv_rn(tpc, __fadd_rn(total, 1e-6f));
-    prec = __fdiv_rn(tpc, __fadd_rn(__fadd_rn(tpc, fpc), 1e-6f));
-}
-
-// one CTA per class: AP = sum of np.trapz terms (float32 each), accumulated in float64
-__global__ void __launch_bounds__(256) ap_kernel(const int *__restrict__ cum, const int64_t *__restrict__ start,
-                                                 const int *__restrict__ gt_per_class, float *__restrict__ ap_out)
-{
-    const int c = blockIdx.x;
-    __shared__ double red[256];
-    const int64_t s0 = start[c], s1 = start[c + 1];
-    const int ngt = gt_per_class[c];
-    double acc = 0.0;
-    if (ngt > 0) {                                                        // utils.py:334-336
-        const float total = static_cast<float>(ngt);
-        const int base = (s0 > 0) ? cum[s0 - 1] : 0;
-        for (int64_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
-            float r1, p1, r0 = 0.0f, p0 = 1.0f;                           // utils.py:438-439
-            pr_point(cum, i, s0, base, total, r1, p1);
-            if (i > s0) pr_point(cum, i - 1, s0, base, total, r0, p0);
-            const float term = __fmul_rn(__fmul_rn(__fsub_rn(r1, r0), __fadd_rn(p1, p0)), 0.5f);   // np.trapz
-            acc += static_cast<double>(term);
-        }
-    }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (static_cast<int>(threadIdx.x) < o) red[threadIdx.x] += red[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) ap_out[c] = static_cast<float>(red[0]);
-}
-
-__global__ void map_mean_kernel(const float *__restrict__ ap, int C, float *__restrict__ out_ap, float *__restrict__ out_map)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int c = 0; c < C; ++c) {
-            s += static_cast<double>(ap[c]);
-            if (out_ap) out_ap[c] = ap[c];
-        }
-        *out_map = static_cast<float>(s / static_cast<double>(C));         // utils.py:456
-    }
-}
-
-// ---- evaluator rows ----------------------------------------------------------------------
-__global__ void rows_append_kernel(const float *__restrict__ boxes, const int *__restrict__ count,
-                                   const int64_t *__restrict__ offs, int64_t n, int M, int64_t img_base,
-                                   float *__restrict__ out_rows, int64_t capacity, const int64_t *__restrict__ cursor)
-{
-    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= n * M) return;
-    const int64_t img = idx / M;
-    const int slot = static_cast<int>(idx % M);
-    if (slot >= count[img]) return;
-    const int64_t row = *cursor + offs[img] + slot;
-    if (row >= capacity) return;
-    const float *b = boxes + idx * 6;
-    float *o = out_rows + row * 7;
-    o[0] = static_cast<float>(img_base + img);                            // utils.py:476
-    o[1] = b[0]; o[2] = b[1]; o[3] = b[2]; o[4] = b[3]; o[5] = b[4]; o[6] = b[5];
-}
-
-__global__ void cursor_advance_kernel(const int *__restrict__ count, const int64_t *__restrict__ offs, int64_t n,
-                                      int64_t *__restrict__ cursor)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cursor += offs[n - 1] + count[n - 1];
-}
-
-struct I32ToI64 {
-    __host__ __device__ int64_t operator()(int v) const { return static_cast<int64_t>(v); }
-};
-
-static inline int blocks_for(int64_t n, int t) { return static_cast<int>((n + t - 1) / t); }
-
-struct AsyncBuf {   // stream-ordered scratch, freed on scope exit
-    cudaStream_t st;
-    void *p = nullptr;
-    explicit AsyncBuf(cudaStream_t s) : st(s) {}
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, st); }
-    ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
-    template <class T> T *as() { return static_cast<T *>(p); }
-};
-
-// The stream-ordered allocator trims its pool at every synchronisation unless a release threshold
-// is set; the evaluator synchronises often (result() returns a host scalar), so keep the scratch.
-static int keep_pool()
+int keep_pool()
 {
     static bool done[64] = {false};
     int dev = 0;
@@ -271,159 +42,399 @@ static int keep_pool()
     return YH_OK;
 }
 
-static int bits_for(int C)
+// ---- single-pass chained scan state --------------------------------------------------------------------------
+constexpr int kScanMaxTiles = 1024;
+constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValMask = (1ull << 62) - 1;
+struct ScanWs {                       // all zero at rest: the last CTA of a launch cleans up after the others
+    unsigned ticket, done, pad0, pad1;
+    unsigned long long st[2][kScanMaxTiles];   // [set][tile]: flag << 62 | value;  set 0 = predictions, 1 = ground truth
+};
+
+// exclusive prefix of tile b >= 1 (sum of the totals of the tiles before it), one full warp, 32 tiles per step
+__device__ __forceinline__ long long lookback(volatile unsigned long long *st, int b, int lane)
 {
-    int b = 1;
-    while ((1ll << b) <= C) ++b;
-    return 32 + b;
+    long long prefix = 0;
+    int hi = b - 1;
+    while (true) {
+        const int j = hi - lane;
+        unsigned long long w = kFlagIncl;                       // before tile 0: inclusive prefix 0
+        if (j >= 0) {
+            do { w = st[j]; } while ((w >> 62) == 0);             // tiles with a lower ticket are running or done
+        }
+        const uint32_t incl = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        const int first = incl ? __ffs(incl) - 1 : 31;            // nearest tile with an inclusive prefix
+        long long v = (lane <= first) ? static_cast<long long>(w & kValMask) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        prefix += v;
+        if (incl) return prefix;
+        hi -= 32;
+    }
+}
+
+struct EvalArgs {
+    const float *boxes[2];            // padded NMS output (n, M, 6): [0] predictions, [1] ground truth (nullable)
+    const int32_t *count[2];          // (n)
+    float *rows[2];                   // (cap, 7) append buffers
+    long long cap[2];
+    long long *cursor[2];             // device row counters
+    unsigned long long *rec;          // (cap[0]) packed records, parallel to the prediction rows (MATCH)
+    int32_t *gt_per_class;            // (C) accumulates (MATCH)
+    long long n, img_base;
+    int M, C, tile;
+    float iou_thr;
+};
+
+template <bool MATCH>
+__global__ void __launch_bounds__(256) eval_update_kernel(EvalArgs a, ScanWs *ws)
+{
+    extern __shared__ int dyn[];                                  // [2][tile] row offsets inside the tile, [C] GT histogram
+    __shared__ int tile_id_s, last_s;
+    __shared__ long long base_s[2];
+    __shared__ int warp_tot[8];
+    __shared__ uint32_t claimed_s[8][YH_MAX_CELLS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nsets = a.boxes[1] ? 2 : 1;
+    const int ntiles = gridDim.x;
+    if (tid == 0) tile_id_s = static_cast<int>(atomicAdd(&ws->ticket, 1u));
+    __syncthreads();
+    const int b = tile_id_s;
+    const long long img0 = static_cast<long long>(b) * a.tile;
+    const int nimg = static_cast<int>(min(static_cast<long long>(a.tile), a.n - img0));
+    int *pre[2] = {dyn, dyn + a.tile};
+    int *hist = dyn + 2 * a.tile;
+    long long agg[2] = {0, 0};
+
+    // ---- 1. kept-row counts of the tile -> offsets inside the tile
+    for (int s = 0; s < nsets; ++s) {
+        int run = 0;
+        for (int i0 = 0; i0 < nimg; i0 += 256) {
+            const int i = i0 + tid;
+            const int c = (i < nimg) ? min(max(a.count[s][img0 + i], 0), a.M) : 0;
+            int v = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (lane == 31) warp_tot[warp] = v;
+            __syncthreads();
+            int woff = 0, all = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int t = warp_tot[w];
+                if (w < warp) woff += t;
+                all += t;
+            }
+            if (i < nimg) pre[s][i] = run + woff + v - c;
+            run += all;
+            __syncthreads();
+        }
+        agg[s] = run;
+    }
+    if (MATCH)
+        for (int c = tid; c < a.C; c += 256) hist[c] = 0;
+
+    // ---- 2. publish the tile total, look back for the row offset of the tile (warp s <-> set s)
+    if (warp < nsets) {
+        const int s = warp;
+        volatile unsigned long long *st = ws->st[s];
+        long long excl;
+        if (b == 0) {
+            excl = *a.cursor[s];                                  // only tile 0 reads the cursor, only the last tile writes it
+        } else {
+            if (lane == 0) st[b] = kFlagAgg | static_cast<unsigned long long>(agg[s]);
+            excl = lookback(st, b, lane);
+        }
+        if (lane == 0) {
+            st[b] = kFlagIncl | static_cast<unsigned long long>(excl + agg[s]);
+            base_s[s] = excl;
+            if (b == ntiles - 1) *a.cursor[s] = excl + agg[s];
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. one warp per image: append the rows (utils.py:476-489), match the image (utils.py:373-422)
+    for (int i = warp; i < nimg; i += 8) {
+        const long long img = img0 + i;
+        const float imgf = static_cast<float>(a.img_base + img);         // utils.py:476: the index travels as float32
+        int cnt[2] = {0, 0};
+        long long row0[2] = {0, 0};
+        for (int s = 0; s < nsets; ++s) {
+            cnt[s] = min(max(a.count[s][img], 0), a.M);
+            row0[s] = base_s[s] + pre[s][i];
+            const float *src = a.boxes[s] + img * a.M * 6;
+            for (int slot = lane; slot < cnt[s]; slot += 32) {
+                const long long r = row0[s] + slot;
+                if (r >= a.cap[s]) continue;
+                const float2 v0 = *reinterpret_cast<const float2 *>(src + slot * 6);
+                const float2 v1 = *reinterpret_cast<const float2 *>(src + slot * 6 + 2);
+                const float2 v2 = *reinterpret_cast<const float2 *>(src + slot * 6 + 4);
+                float *o = a.rows[s] + r * 7;
+                o[0] = imgf; o[1] = v0.x; o[2] = v0.y; o[3] = v1.x; o[4] = v1.y; o[5] = v2.x; o[6] = v2.y;
+            }
+        }
+        if (!MATCH) continue;
+        const float *pb = a.boxes[0] + img * a.M * 6;
+        const float *tb = a.boxes[1] + img * a.M * 6;
+        const int np_i = cnt[0], nt_i = cnt[1];
+        if (lane < YH_MAX_CELLS / 32) claimed_s[warp][lane] = 0;
+        for (int g = lane; g < nt_i; g += 32) {
+            const uint32_t gc = class_of(tb[g * 6], a.C);
+            if (gc < static_cast<uint32_t>(a.C)) atomicAdd(&hist[gc], 1);            // utils.py:330 rows of the class
+        }
+        __syncwarp();
+        for (int d0 = 0; d0 < np_i; d0 += 32) {
+            const int d = d0 + lane;
+            const bool valid = d < np_i;
+            float conf = 0.0f, dx = 0.0f, dy = 0.0f, dw = 0.0f, dh = 0.0f;
+            uint32_t dc = static_cast<uint32_t>(a.C);
+            if (valid) {
+                const float2 v0 = *reinterpret_cast<const float2 *>(pb + d * 6);
+                const float2 v1 = *reinterpret_cast<const float2 *>(pb + d * 6 + 2);
+                const float2 v2 = *reinterpret_cast<const float2 *>(pb + d * 6 + 4);
+                dc = class_of(v0.x, a.C);
+                conf = v0.y; dx = v1.x; dy = v1.y; dw = v2.x; dh = v2.y;
+            }
+            float best = 0.0f;                                               // utils.py:382 (unwritten slot reads 0)
+            int bj = 0;                                                      // utils.py:383
+            for (int g0 = 0; g0 < nt_i; g0 += 32) {
+                const int g = g0 + lane;
+                uint32_t gc = 0xffffffffu;
+                float gx = 0.0f, gy = 0.0f, gw = 0.0f, gh = 0.0f;
+                if (g < nt_i) {
+                    const float2 v0 = *reinterpret_cast<const float2 *>(tb + g * 6);
+                    const float2 v1 = *reinterpret_cast<const float2 *>(tb + g * 6 + 2);
+                    const float2 v2 = *reinterpret_cast<const float2 *>(tb + g * 6 + 4);
+                    gc = class_of(v0.x, a.C);
+                    gx = v1.x; gy = v1.y; gw = v2.x; gh = v2.y;
+                }
+                const int lim = min(32, nt_i - g0);
+                for (int k = 0; k < lim; ++k) {                              // utils.py:386: ground truths of the image in row order
+                    const uint32_t kc = __shfl_sync(0xffffffffu, gc, k);
+                    const float kx = __shfl_sync(0xffffffffu, gx, k), ky = __shfl_sync(0xffffffffu, gy, k);
+                    const float kw = __shfl_sync(0xffffffffu, gw, k), kh = __shfl_sync(0xffffffffu, gh, k);
+                    if (kc == dc && dc < static_cast<uint32_t>(a.C)) {
+                        const float v = iou_ref(dx, dy, dw, dh, kx, ky, kw, kh);         // utils.py:387 (det, gt)
+                        if (v > best) { best = v; bj = g0 + k; }                        // utils.py:389
+                    }
+                }
+            }
+            const bool hit = valid && best > a.iou_thr;                                // utils.py:395
+            const bool taken = hit && ((claimed_s[warp][bj >> 5] >> (bj & 31)) & 1u);  // claimed by an earlier chunk
+            const uint32_t peers = __match_any_sync(0xffffffffu, (hit && !taken) ? static_cast<uint32_t>(bj) : 0x10000u + lane);
+            const bool tp = hit && !taken && lane == __ffs(peers) - 1;                 // utils.py:408-418: first in order claims
+            __syncwarp();
+            if (tp) atomicOr(&claimed_s[warp][bj >> 5], 1u << (bj & 31));
+            __syncwarp();
+            if (valid) {
+                const long long r = row0[0] + d;
+                if (r < a.cap[0]) a.rec[r] = make_rec(dc, conf, tp ? 1u : 0u);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (MATCH)
+        for (int c = tid; c < a.C; c += 256)
+            if (hist[c]) atomicAdd(a.gt_per_class + c, hist[c]);
+
+    // ---- 4. the last CTA to finish returns the scan state to all-zero
+    if (tid == 0) {
+        __threadfence();
+        last_s = (atomicAdd(&ws->done, 1u) == static_cast<unsigned>(ntiles - 1));
+    }
+    __syncthreads();
+    if (last_s) {
+        for (int j = tid; j < ntiles; j += 256) { ws->st[0][j] = 0; ws->st[1][j] = 0; }
+        if (tid == 0) { ws->ticket = 0; ws->done = 0; }
+    }
+}
+
+// scan state per (device, stream): launches on one stream are ordered, so they can share it
+static std::mutex g_scan_mu;
+static std::map<std::pair<int, cudaStream_t>, ScanWs *> g_scan_ws;
+
+static int scan_ws_for(cudaStream_t st, ScanWs **out)
+{
+    int dev = 0;
+    YH_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_scan_mu);
+    auto key = std::make_pair(dev, st);
+    auto it = g_scan_ws.find(key);
+    if (it == g_scan_ws.end()) {
+        ScanWs *p = nullptr;
+        YH_CUDA(cudaMalloc(&p, sizeof(ScanWs)));
+        cudaError_t e = cudaMemsetAsync(p, 0, sizeof(ScanWs), st);
+        if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaMemsetAsync"); }
+        it = g_scan_ws.emplace(key, p).first;
+    }
+    *out = it->second;
+    return YH_OK;
+}
+
+static int eval_update_impl(EvalArgs a, bool match, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScanWs *ws = nullptr;
+    int rc = scan_ws_for(st, &ws);
+    if (rc != YH_OK) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        YH_CUDA(cudaFuncSetAttribute(eval_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        YH_CUDA(cudaFuncSetAttribute(eval_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
+    }
+    const long long n_all = a.n, base_all = a.img_base;
+    const float *boxes0[2] = {a.boxes[0], a.boxes[1]};
+    const int32_t *count0[2] = {a.count[0], a.count[1]};
+    const long long chunk = static_cast<long long>(kScanMaxTiles) * 1024;       // images per launch
+    for (long long lo = 0; lo < n_all; lo += chunk) {
+        a.n = std::min(chunk, n_all - lo);
+        a.img_base = base_all + lo;
+        for (int s = 0; s < 2; ++s) {
+            a.boxes[s] = boxes0[s] ? boxes0[s] + lo * a.M * 6 : nullptr;
+            a.count[s] = count0[s] ? count0[s] + lo : nullptr;
+        }
+        // tiles: enough CTAs to fill the machine four times over, at most kScanMaxTiles, a multiple of 8 images each
+        long long tile = (a.n + 4 * sm_count() - 1) / (4 * sm_count());
+        tile = std::max<long long>(8, std::min<long long>(1024, (tile + 7) / 8 * 8));
+        a.tile = static_cast<int>(tile);
+        const int ntiles = static_cast<int>((a.n + tile - 1) / tile);
+        const size_t smem = sizeof(int) * (2 * static_cast<size_t>(a.tile) + (match ? a.C : 0));
+        if (match) eval_update_kernel<true><<<ntiles, 256, smem, st>>>(a, ws);
+        else eval_update_kernel<false><<<ntiles, 256, smem, st>>>(a, ws);
+        YH_LAUNCH_CHECK("eval_update_kernel");
+    }
+    return YH_OK;
+}
+
+// ---- general path: arbitrary rows ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) map_prep_kernel(const float *__restrict__ true_rows, long long nt_max,
+                                                       const long long *__restrict__ nt_dev, int C,
+                                                       unsigned long long *__restrict__ claim, unsigned long long *__restrict__ gk,
+                                                       int32_t *__restrict__ gt_per_class)
+{
+    extern __shared__ int hist[];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) hist[c] = 0;
+    __syncthreads();
+    const long long nt = nt_dev ? min(max(*nt_dev, 0ll), nt_max) : nt_max;
+    for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < nt;
+         g += static_cast<long long>(gridDim.x) * blockDim.x) {
+        claim[g] = ~0ull;
+        const uint32_t c = class_of(true_rows[7 * g + 1], C);
+        if (c < static_cast<uint32_t>(C)) atomicAdd(&hist[c], 1);
+        if (gk) gk[g] = (static_cast<unsigned long long>(orderable(true_rows[7 * g])) << 32) | static_cast<unsigned long long>(g);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        if (hist[c]) atomicAdd(gt_per_class + c, hist[c]);
+}
+
+// one thread per detection.  Ground truths of an image: rows [lo, ...) with the image's key, either in the rows
+// themselves (grouped by image, nondecreasing) or through the sorted (image key << 32 | row) list gk.
+__global__ void __launch_bounds__(128) map_match_kernel(const float *__restrict__ true_rows, long long nt_max,
+                                                        const long long *__restrict__ nt_dev, const float *__restrict__ pred_rows,
+                                                        long long np_max, const long long *__restrict__ np_dev, int C, float iou_thr,
+                                                        const unsigned long long *__restrict__ gk, const long long *__restrict__ gk_n,
+                                                        unsigned long long *__restrict__ claim, int32_t *__restrict__ hit)
+{
+    const long long np = np_dev ? min(max(*np_dev, 0ll), np_max) : np_max;
+    long long nt = nt_dev ? min(max(*nt_dev, 0ll), nt_max) : nt_max;
+    if (gk && gk_n) nt = *gk_n;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < np;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float *d = pred_rows + 7 * i;
+        const uint32_t dc = class_of(d[1], C);
+        int32_t h = -1;
+        if (dc < static_cast<uint32_t>(C)) {
+            const uint32_t ik = orderable(d[0]);
+            long long lo = 0, hi = nt;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                const uint32_t mk = gk ? static_cast<uint32_t>(gk[mid] >> 32) : orderable(true_rows[7 * mid]);
+                if (mk < ik) lo = mid + 1; else hi = mid;
+            }
+            const float dx = d[3], dy = d[4], dw = d[5], dh = d[6];
+            float best = 0.0f;                               // utils.py:382
+            long long bj = 0;                                // utils.py:383
+            for (long long m = lo; m < nt; ++m) {            // utils.py:386: row order inside the image
+                long long g = m;
+                if (gk) {
+                    const unsigned long long e = gk[m];
+                    if (static_cast<uint32_t>(e >> 32) != ik) break;
+                    g = static_cast<long long>(e & 0xffffffffull);
+                } else if (orderable(true_rows[7 * m]) != ik) {
+                    break;
+                }
+                const float *t = true_rows + 7 * g;
+                if (class_of(t[1], C) != dc) continue;       // utils.py:330, :378
+                const float v = iou_ref(dx, dy, dw, dh, t[3], t[4], t[5], t[6]);    // utils.py:387 (det, gt)
+                if (v > best) { best = v; bj = g; }          // utils.py:389
+            }
+            if (best > iou_thr) {                            // utils.py:395
+                h = static_cast<int32_t>(bj);
+                atomicMin(claim + bj, (static_cast<unsigned long long>(~orderable(d[2])) << 32) | static_cast<unsigned long long>(i));
+            }
+        }
+        hit[i] = h;
+    }
+}
+
+__global__ void __launch_bounds__(256) map_tp_kernel(const float *__restrict__ pred_rows, long long np_max,
+                                                     const long long *__restrict__ np_dev, int C,
+                                                     const int32_t *__restrict__ hit, const unsigned long long *__restrict__ claim,
+                                                     unsigned long long *__restrict__ rec)
+{
+    const long long np = np_dev ? min(max(*np_dev, 0ll), np_max) : np_max;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < np;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float conf = pred_rows[7 * i + 2];
+        const int32_t h = hit[i];
+        const unsigned long long mine = (static_cast<unsigned long long>(~orderable(conf)) << 32) | static_cast<unsigned long long>(i);
+        const uint32_t tp = (h >= 0 && claim[h] == mine) ? 1u : 0u;               // utils.py:408-418
+        rec[i] = make_rec(class_of(pred_rows[7 * i + 1], C), conf, tp);
+    }
+}
+
+static inline int blocks_for(long long n, int t, int cap)
+{
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((n + t - 1) / t, cap)));
+}
+
+size_t match_ws_bytes(int64_t nt, int64_t np, bool sorted)
+{
+    size_t b = align_up(static_cast<size_t>(nt) * 8, 256) + align_up(static_cast<size_t>(np) * 4, 256) + 256;
+    if (!sorted) b += align_up(static_cast<size_t>(nt) * 8, 256) + radix_ws_bytes(nt, 1);
+    return b;
 }
 
 }  // namespace yh
 
 using namespace yh;
 
-static int map_match_impl(const float *true_rows, int64_t nt, const float *pred_rows, int64_t np, int C, float iou_thr,
-                          uint64_t *out_keys, uint8_t *out_tp, int32_t *out_gt_per_class, void *stream, const PeerSet *peers)
+extern "C" int yh_eval_update(const float *pred_boxes, const int32_t *pred_count, const float *true_boxes,
+                              const int32_t *true_count, int64_t n, int M, int64_t img_base, int C, float iou_thr,
+                              float *pred_rows, int64_t pred_capacity, float *true_rows, int64_t true_capacity,
+                              uint64_t *rec, int64_t *cursors, int32_t *gt_per_class, void *stream)
 {
-    YH_REQUIRE(C >= 1 && nt >= 0 && np >= 0, "map_match: bad sizes");
-    YH_REQUIRE(nt < (1ll << 31) && np < (1ll << 31), "map_match: more than 2^31 rows");
-    YH_REQUIRE(out_gt_per_class != nullptr, "map_match: out_gt_per_class is null");
-    YH_REQUIRE((nt == 0 || true_rows) && (np == 0 || (pred_rows && out_keys && out_tp)), "map_match: null pointer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
-    YH_CUDA(cudaMemsetAsync(out_gt_per_class, 0, sizeof(int32_t) * C, st));
-    const int end_bit = bits_for(C);
-
-    AsyncBuf gk_in(st), gv_in(st), gk(st), gv(st), dk_in(st), dv_in(st), dv(st), claim(st), hit(st), tmp(st);
-    YH_CUDA(gk_in.alloc(8 * nt)); YH_CUDA(gv_in.alloc(4 * nt)); YH_CUDA(gk.alloc(8 * nt)); YH_CUDA(gv.alloc(4 * nt));
-    YH_CUDA(dk_in.alloc(8 * np)); YH_CUDA(dv_in.alloc(4 * np)); YH_CUDA(dv.alloc(4 * np));
-    YH_CUDA(claim.alloc(4 * nt)); YH_CUDA(hit.alloc(4 * np));
-
-    if (nt > 0) {
-        gt_keys_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(true_rows, nt, C, gk_in.as<uint64_t>(), gv_in.as<uint32_t>(),
-                                                            out_gt_per_class);
-        YH_LAUNCH_CHECK("gt_keys_kernel");
-    }
-    if (peers && peers->has_gt) {
-        gt_scatter_kernel<<<blocks_for(C, 128), 128, 0, st>>>(out_gt_per_class, C, *peers);
-        YH_LAUNCH_CHECK("gt_scatter_kernel");
-    }
-    if (np == 0) return YH_OK;
-    det_keys_kernel<<<blocks_for(np, 256), 256, 0, st>>>(pred_rows, np, C, dk_in.as<uint64_t>(), dv_in.as<uint32_t>());
-    YH_LAUNCH_CHECK("det_keys_kernel");
-
-    size_t tb1 = 0, tb2 = 0;
-    YH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb1, gk_in.as<uint64_t>(), gk.as<uint64_t>(), gv_in.as<uint32_t>(),
-                                            gv.as<uint32_t>(), static_cast<int>(nt), 0, end_bit, st));
-    YH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk_in.as<uint64_t>(), out_keys, dv_in.as<uint32_t>(),
-                                            dv.as<uint32_t>(), static_cast<int>(np), 0, end_bit, st));
-    YH_CUDA(tmp.alloc(std::max(tb1, tb2)));
-    size_t tb = std::max(tb1, tb2);
-    if (nt > 0) {
-        YH_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, gk_in.as<uint64_t>(), gk.as<uint64_t>(), gv_in.as<uint32_t>(),
-                                                gv.as<uint32_t>(), static_cast<int>(nt), 0, end_bit, st));
-        count_launch(4);
-        YH_CUDA(cudaMemsetAsync(claim.p, 0xff, 4 * nt, st));
-    }
-    tb = std::max(tb1, tb2);
-    YH_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk_in.as<uint64_t>(), out_keys, dv_in.as<uint32_t>(),
-                                            dv.as<uint32_t>(), static_cast<int>(np), 0, end_bit, st));
-    count_launch(4);
-    match_kernel<<<blocks_for(np, 128), 128, 0, st>>>(pred_rows, dv.as<uint32_t>(), out_keys, np, true_rows,
-                                                      gk.as<uint64_t>(), gv.as<uint32_t>(), nt, C, iou_thr,
-                                                      hit.as<int32_t>(), claim.as<uint32_t>());
-    YH_LAUNCH_CHECK("match_kernel");
-    if (peers) {
-        tp_scatter_kernel<<<blocks_for(np, 256), 256, 0, st>>>(hit.as<int32_t>(), claim.as<uint32_t>(), np, *peers);
-        YH_LAUNCH_CHECK("tp_scatter_kernel");
-    } else {
-        tp_kernel<<<blocks_for(np, 256), 256, 0, st>>>(hit.as<int32_t>(), claim.as<uint32_t>(), np, out_tp);
-        YH_LAUNCH_CHECK("tp_kernel");
-    }
-    return YH_OK;
-}
-
-extern "C" int yh_map_match(const float *true_rows, int64_t nt, const float *pred_rows, int64_t np, int C, float iou_thr,
-                            uint64_t *out_keys, uint8_t *out_tp, int32_t *out_gt_per_class, void *stream)
-{
-    return map_match_impl(true_rows, nt, pred_rows, np, C, iou_thr, out_keys, out_tp, out_gt_per_class, stream, nullptr);
-}
-
-// Stage 1 fused with the exchange step over peer-mapped memory: this device (index `self` of `n_peers`) matches its
-// shard and stores its records at [offset, offset + np) of EVERY peer's record buffers.  The pointers may come from
-// cudaDeviceEnablePeerAccess in one process (yh_map_match_p2p) or from CUDA IPC handles of other processes (yh_ipc_open).
-// gt_sum_all (nullable): per-device accumulators that receive this shard's per-class GT counts by system-scope atomics;
-// out_gt_local (nullable): the shard's own counts (for a caller that sums them itself).
-extern "C" int yh_map_match_peers(int n_peers, int self, const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
-                                  int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
-                                  int32_t *const *gt_sum_all, int32_t *out_gt_local, void *stream)
-{
-    YH_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && self >= 0 && self < n_peers && offset >= 0,
-               "map_match_peers: bad peer count / index / offset (at most %d peers)", kMaxPeers);
-    YH_REQUIRE(C >= 1 && out_keys_all && out_tp_all, "map_match_peers: null pointer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PeerSet ps;
-    ps.n = n_peers; ps.self = self; ps.offset = offset;
-    for (int d = 0; d < n_peers; ++d) {
-        ps.keys[d] = out_keys_all[d]; ps.tp[d] = out_tp_all[d]; ps.gt[d] = gt_sum_all ? gt_sum_all[d] : nullptr;
-        YH_REQUIRE((!gt_sum_all || ps.gt[d]) && (np == 0 || (ps.keys[d] && ps.tp[d])), "map_match_peers: null buffer for peer %d", d);
-    }
-    ps.has_gt = gt_sum_all ? 1 : 0;
-    AsyncBuf gt_tmp(st);
-    int32_t *gt_local = out_gt_local;
-    if (!gt_local) {
-        YH_CUDA(gt_tmp.alloc(sizeof(int32_t) * C));
-        gt_local = gt_tmp.as<int32_t>();
-    }
-    return map_match_impl(true_rows, nt, pred_rows, np, C, iou_thr, ps.keys[self] + offset, ps.tp[self] + offset, gt_local,
-                          stream, &ps);
-}
-
-// Single-process flavour: the peers are the devices of a communicator (peer access enabled by yh_comm_init_all).
-extern "C" int yh_map_match_p2p(void *comm, int dev_index, const float *true_rows, int64_t nt, const float *pred_rows, int64_t np,
-                                int C, float iou_thr, uint64_t *const *out_keys_all, uint8_t *const *out_tp_all, int64_t offset,
-                                int32_t *const *gt_sum_all, void *stream)
-{
-    YH_REQUIRE(comm != nullptr, "map_match_p2p: null communicator");
-    const Comm *c = static_cast<const Comm *>(comm);
-    YH_REQUIRE(c->p2p, "map_match_p2p: the devices of this communicator cannot access each other's memory; use yh_map_allgather");
-    YH_REQUIRE(dev_index >= 0 && dev_index < c->ndev && gt_sum_all, "map_match_p2p: bad device index / null pointer");
-    return yh_map_match_peers(c->ndev, dev_index, true_rows, nt, pred_rows, np, C, iou_thr, out_keys_all, out_tp_all, offset,
-                              gt_sum_all, nullptr, stream);
-}
-
-extern "C" int yh_map_reduce(const uint64_t *keys, const uint8_t *tp, int64_t nrec, const int32_t *gt_per_class, int C,
-                             float *out_ap, float *out_map, void *stream)
-{
-    YH_REQUIRE(C >= 1 && nrec >= 0 && nrec < (1ll << 31), "map_reduce: bad sizes");
-    YH_REQUIRE(gt_per_class && out_map && (nrec == 0 || (keys && tp)), "map_reduce: null pointer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
-    const int end_bit = bits_for(C);
-    AsyncBuf sk(st), stp(st), cum(st), start(st), ap(st), tmp(st);
-    YH_CUDA(sk.alloc(8 * nrec)); YH_CUDA(stp.alloc(nrec)); YH_CUDA(cum.alloc(4 * nrec));
-    YH_CUDA(start.alloc(8 * (C + 1))); YH_CUDA(ap.alloc(4 * C));
-    if (nrec > 0) {
-        size_t tb1 = 0, tb2 = 0;
-        YH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb1, keys, sk.as<uint64_t>(), tp, stp.as<uint8_t>(),
-                                                static_cast<int>(nrec), 0, end_bit, st));
-        cub::TransformInputIterator<int, U8ToI32, const uint8_t *> it(stp.as<uint8_t>(), U8ToI32());
-        YH_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb2, it, cum.as<int>(), static_cast<int>(nrec), st));
-        YH_CUDA(tmp.alloc(std::max(tb1, tb2)));
-        size_t tb = std::max(tb1, tb2);
-        YH_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys, sk.as<uint64_t>(), tp, stp.as<uint8_t>(),
-                                                static_cast<int>(nrec), 0, end_bit, st));
-        tb = std::max(tb1, tb2);
-        YH_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, it, cum.as<int>(), static_cast<int>(nrec), st));
-        count_launch(6);
-    }
-    class_starts_kernel<<<blocks_for(C + 1, 128), 128, 0, st>>>(sk.as<uint64_t>(), nrec, C, start.as<int64_t>());
-    YH_LAUNCH_CHECK("class_starts_kernel");
-    ap_kernel<<<C, 256, 0, st>>>(cum.as<int>(), start.as<int64_t>(), gt_per_class, ap.as<float>());
-    YH_LAUNCH_CHECK("ap_kernel");
-    map_mean_kernel<<<1, 32, 0, st>>>(ap.as<float>(), C, out_ap, out_map);
-    YH_LAUNCH_CHECK("map_mean_kernel");
-    return YH_OK;
+    YH_REQUIRE(n >= 0 && M >= 1 && M <= YH_MAX_CELLS, "eval_update: bad sizes (M = %d, limit %d)", M, YH_MAX_CELLS);
+    YH_REQUIRE(C >= 1 && C <= kMaxMapClasses, "eval_update: C = %d outside [1, %d]", C, kMaxMapClasses);
+    if (n == 0) return YH_OK;
+    YH_REQUIRE(pred_boxes && pred_count && true_boxes && true_count && cursors && rec && gt_per_class,
+               "eval_update: null pointer");
+    YH_REQUIRE(pred_capacity >= 0 && true_capacity >= 0 && (pred_capacity == 0 || pred_rows) && (true_capacity == 0 || true_rows),
+               "eval_update: bad row buffers");
+    EvalArgs a{};
+    a.boxes[0] = pred_boxes; a.boxes[1] = true_boxes;
+    a.count[0] = pred_count; a.count[1] = true_count;
+    a.rows[0] = pred_rows; a.rows[1] = true_rows;
+    a.cap[0] = pred_capacity; a.cap[1] = true_capacity;
+    a.cursor[0] = reinterpret_cast<long long *>(cursors); a.cursor[1] = reinterpret_cast<long long *>(cursors) + 1;
+    a.rec = reinterpret_cast<unsigned long long *>(rec);
+    a.gt_per_class = gt_per_class;
+    a.n = n; a.img_base = img_base; a.M = M; a.C = C; a.iou_thr = iou_thr;
+    return eval_update_impl(a, true, stream);
 }
 
 extern "C" int yh_rows_append(const float *boxes, const int32_t *count, int64_t n, int M, int64_t img_base,
@@ -432,21 +443,69 @@ extern "C" int yh_rows_append(const float *boxes, const int32_t *count, int64_t 
     YH_REQUIRE(n >= 0 && M >= 1 && out_capacity >= 0, "rows_append: bad sizes");
     if (n == 0) return YH_OK;
     YH_REQUIRE(boxes && count && row_cursor && (out_capacity == 0 || out_rows), "rows_append: null pointer");
-    YH_REQUIRE(n < (1ll << 31), "rows_append: too many images in one call");
+    EvalArgs a{};
+    a.boxes[0] = boxes; a.count[0] = count; a.rows[0] = out_rows; a.cap[0] = out_capacity;
+    a.cursor[0] = reinterpret_cast<long long *>(row_cursor);
+    a.n = n; a.img_base = img_base; a.M = M; a.C = 1; a.iou_thr = 0.0f;
+    return eval_update_impl(a, false, stream);
+}
+
+extern "C" int yh_map_match(const float *true_rows, int64_t nt, const int64_t *nt_dev, const float *pred_rows, int64_t np,
+                            const int64_t *np_dev, int C, float iou_thr, int flags, uint64_t *out_rec,
+                            int32_t *out_gt_per_class, void *workspace, size_t workspace_bytes, void *stream)
+{
+    YH_REQUIRE(C >= 1 && C <= kMaxMapClasses, "map_match: C = %d outside [1, %d]", C, kMaxMapClasses);
+    YH_REQUIRE(nt >= 0 && np >= 0 && nt < (1ll << 31) && np < (1ll << 31), "map_match: bad row counts");
+    YH_REQUIRE(out_gt_per_class != nullptr, "map_match: out_gt_per_class is null");
+    YH_REQUIRE((nt == 0 || true_rows) && (np == 0 || (pred_rows && out_rec)), "map_match: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    { int rc_ = keep_pool(); if (rc_ != YH_OK) return rc_; }
-    AsyncBuf offs(st), tmp(st);
-    YH_CUDA(offs.alloc(8 * n));
-    size_t tb = 0;
-    cub::TransformInputIterator<int64_t, I32ToI64, const int *> it(count, I32ToI64());
-    YH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, offs.as<int64_t>(), static_cast<int>(n), st));
-    YH_CUDA(tmp.alloc(tb));
-    YH_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, it, offs.as<int64_t>(), static_cast<int>(n), st));
-    count_launch(2);
-    rows_append_kernel<<<blocks_for(n * M, 256), 256, 0, st>>>(boxes, count, offs.as<int64_t>(), n, M, img_base, out_rows,
-                                                               out_capacity, row_cursor);
-    YH_LAUNCH_CHECK("rows_append_kernel");
-    cursor_advance_kernel<<<1, 32, 0, st>>>(count, offs.as<int64_t>(), n, row_cursor);
-    YH_LAUNCH_CHECK("cursor_advance_kernel");
+    const bool sorted = (flags & YH_MAP_TRUE_ROWS_BY_IMAGE) != 0;
+    AsyncBuf own(st);
+    const size_t need = match_ws_bytes(nt, np, sorted);
+    if (!workspace) {
+        int rc = keep_pool();
+        if (rc != YH_OK) return rc;
+        YH_CUDA(own.alloc(need));
+        workspace = own.p;
+        workspace_bytes = need;
+    }
+    YH_REQUIRE(workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "map_match: a 256-byte aligned workspace of %zu bytes is needed", need);
+    unsigned char *w = static_cast<unsigned char *>(workspace);
+    unsigned long long *claim = reinterpret_cast<unsigned long long *>(w); w += align_up(static_cast<size_t>(nt) * 8, 256);
+    int32_t *hit = reinterpret_cast<int32_t *>(w); w += align_up(static_cast<size_t>(np) * 4, 256);
+    long long *gk_n = reinterpret_cast<long long *>(w); w += 256;
+    unsigned long long *gk = nullptr;
+    if (!sorted) { gk = reinterpret_cast<unsigned long long *>(w); w += align_up(static_cast<size_t>(nt) * 8, 256); }
+
+    YH_CUDA(cudaMemsetAsync(out_gt_per_class, 0, sizeof(int32_t) * C, st));
+    const int cap = 8 * sm_count();
+    map_prep_kernel<<<blocks_for(nt, 256, cap), 256, sizeof(int) * C, st>>>(true_rows, nt, reinterpret_cast<const long long *>(nt_dev), C,
+                                                                             claim, gk, out_gt_per_class);
+    YH_LAUNCH_CHECK("map_prep_kernel");
+    if (np == 0) return YH_OK;
+    const unsigned long long *gk_sorted = nullptr;
+    if (!sorted) {                                   // ground-truth rows in any order: stable radix sort by image
+        ReduceArgs ra{};
+        ra.in.nseg = 1;
+        ra.in.ptr[0] = gk;
+        ra.in.cnt_dev[0] = reinterpret_cast<const long long *>(nt_dev);
+        ra.in.cnt_max[0] = nt;
+        ra.bit_lo = 32;
+        ra.npass = 4;
+        ra.mode = YH_RADIX_SORT_ONLY;
+        ra.C = 1;
+        ra.out_n = gk_n;
+        int rc = radix_launch(ra, nt, w, radix_ws_bytes(nt, 1), st);
+        if (rc != YH_OK) return rc;
+        gk_sorted = ra.buf[(ra.npass - 1) & 1];
+    }
+    map_match_kernel<<<blocks_for(np, 128, 16 * sm_count()), 128, 0, st>>>(
+        true_rows, nt, reinterpret_cast<const long long *>(nt_dev), pred_rows, np, reinterpret_cast<const long long *>(np_dev), C,
+        iou_thr, gk_sorted, gk_sorted ? gk_n : nullptr, claim, hit);
+    YH_LAUNCH_CHECK("map_match_kernel");
+    map_tp_kernel<<<blocks_for(np, 256, cap), 256, 0, st>>>(pred_rows, np, reinterpret_cast<const long long *>(np_dev), C, hit, claim,
+                                                             reinterpret_cast<unsigned long long *>(out_rec));
+    YH_LAUNCH_CHECK("map_tp_kernel");
     return YH_OK;
 }

@@ -13,6 +13,9 @@ LIB_PATH = os.environ.get("YH_LIB_PATH") or os.path.join(_HERE, "libyolohot.so")
 YH_OK, YH_ERR_ARG, YH_ERR_CUDA, YH_ERR_NCCL, YH_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 YH_IPC_HANDLE_BYTES = 64
 YH_DTYPE_F32, YH_DTYPE_F16, YH_DTYPE_BF16 = 0, 1, 2
+YH_MAP_TRUE_ROWS_BY_IMAGE = 1
+YH_MAP_ERR_TIMEOUT, YH_MAP_ERR_OVERFLOW = 1, 2
+YH_OP_DECODE_NMS, YH_OP_DECODE_NMS_HOST, YH_OP_LOSS, YH_OP_MAP_MATCH, YH_OP_MAP_REDUCE = 1, 2, 3, 4, 5
 
 _lib = None
 
@@ -20,9 +23,10 @@ _lib = None
 SYMBOLS = (
     "yh_version", "yh_last_error", "yh_device_info", "yh_launch_count",
     "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_ex", "yh_decode_nms_host", "yh_decode_nms_host_typed", "yh_filter_rows", "yh_rows_append",
-    "yh_loss", "yh_map_match", "yh_map_reduce",
+    "yh_loss", "yh_eval_update", "yh_map_match", "yh_map_reduce",
     "yh_encode_labels", "yh_head_to_f32", "yh_decode_nms_typed", "yh_pixel_boxes",
-    "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_comm_p2p", "yh_comm_barrier", "yh_map_match_p2p", "yh_map_match_peers",
+    "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_comm_p2p", "yh_comm_barrier",
+    "yh_map_exchange_bytes", "yh_map_exchange", "yh_map_reduce_exchanged",
     "yh_ipc_alloc", "yh_ipc_open", "yh_ipc_close", "yh_ipc_free",
     "yh_workspace_bytes",
     "yh_iou_dl", "yh_decode_dl", "yh_nms_dl", "yh_decode_nms_dl", "yh_loss_dl",
@@ -58,19 +62,22 @@ def lib():
     L.yh_filter_rows.argtypes = [vp, i64, i, f, vp, vp, vp]
     L.yh_rows_append.argtypes = [vp, vp, i64, i, i64, vp, i64, vp, vp]
     L.yh_loss.argtypes = [vp, vp, i64, i, i, f, f, vp, vp, vp]
-    L.yh_map_match.argtypes = [vp, i64, vp, i64, i, f, vp, vp, vp, vp]
-    L.yh_map_reduce.argtypes = [vp, vp, i64, vp, i, vp, vp, vp]
+    L.yh_eval_update.argtypes = [vp, vp, vp, vp, i64, i, i64, i, f, vp, i64, vp, i64, vp, vp, vp, vp]
+    L.yh_map_match.argtypes = [vp, i64, vp, vp, i64, vp, i, f, i, vp, vp, vp, C.c_size_t, vp]
+    L.yh_map_reduce.argtypes = [vp, i64, vp, i64, vp, i, vp, vp, vp, C.c_size_t, vp]
+    L.yh_map_exchange_bytes.argtypes = [i, i, i64]
+    L.yh_map_exchange_bytes.restype = C.c_size_t
+    L.yh_map_exchange.argtypes = [i, i, vp, i, i64, vp, i64, vp, vp, C.c_uint64, vp]
+    L.yh_map_reduce_exchanged.argtypes = [i, vp, i, i64, C.c_uint64, i64, vp, vp, vp, vp, C.c_size_t, vp]
     L.yh_encode_labels.argtypes = [vp, vp, i64, i, i, i, vp, vp, vp]
     L.yh_head_to_f32.argtypes = [vp, i, i64, vp, vp]
     L.yh_decode_nms_typed.argtypes = [vp, i, i64, i, i, i, f, f, i, vp, vp, vp, vp]
     L.yh_pixel_boxes.argtypes = [vp, vp, i64, i, i, i, vp, vp]
     L.yh_comm_init_all.argtypes = [i, vp, vp]
     L.yh_comm_destroy.argtypes = [vp]
-    L.yh_map_allgather.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, i64, vp]
+    L.yh_map_allgather.argtypes = [vp, vp, vp, vp, i, vp, i64, vp]
     L.yh_comm_p2p.argtypes = [vp]
     L.yh_comm_barrier.argtypes = [vp, vp]
-    L.yh_map_match_p2p.argtypes = [vp, i, vp, i64, vp, i64, i, f, vp, vp, i64, vp, vp]
-    L.yh_map_match_peers.argtypes = [i, i, vp, i64, vp, i64, i, f, vp, vp, i64, vp, vp, vp]
     L.yh_ipc_alloc.argtypes = [C.c_size_t, vp, vp]
     L.yh_ipc_open.argtypes = [vp, vp]
     L.yh_ipc_close.argtypes = [vp]
@@ -84,7 +91,7 @@ def lib():
     L.yh_loss_dl.argtypes = [vp, vp, i, i, f, f, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(L, s)
-        if s not in ("yh_version", "yh_last_error", "yh_launch_count", "yh_workspace_bytes"):
+        if s not in ("yh_version", "yh_last_error", "yh_launch_count", "yh_workspace_bytes", "yh_map_exchange_bytes"):
             fn.restype = i
     _lib = L
     return L

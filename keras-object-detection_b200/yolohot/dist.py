@@ -1,31 +1,32 @@
 """Multi-GPU plumbing of the mAP reduction: one process per GPU (torch.distributed, NCCL over
 NVLink on a B200 box; gloo in the CPU tests).  The decode / NMS / loss / matching kernels
 need no communication - images are sharded by contiguous range - so the only exchange is
-  (1) all-reduce(sum) of the per-class ground-truth counts (C int32), and
-  (2) all-gather of the per-detection records (uint64 sort key, uint8 TP flag), padded to the
-      largest shard, concatenated IN RANK ORDER (rank order == image order, which the stable
-      sort of stage 2 relies on for equal confidences).
-Volume is <= 9 B x detections (a few MB at most): latency-bound.
+  (1) the per-class ground-truth counts (C int32 per rank, summed), and
+  (2) the per-detection records (one packed uint64: class, confidence, TP flag), concatenated IN RANK
+      ORDER (rank order == image order, which the stable sort of stage 2 relies on for equal confidences).
+Volume is 8 B x detections (a few MB at most): latency-bound.
 
-Two implementations of (2):
-  gather_records   padded all-gathers through torch.distributed (NCCL, or gloo on CPU);
-  PeerExchange     NCCL ranks of ONE box: every rank owns record buffers that its peers map through CUDA IPC, and the
-                   last kernel of the matching stage stores each record straight into all of them over NVLink
-                   (yh_map_match_peers) - the exchange is fused into the compute kernel.  What is left on NCCL is the
-                   control plane: an all-gather of the shard sizes (gives the offsets and orders the reuse of the
-                   buffers) and the all-reduce of (1), which also orders the peers' stores before stage 2."""
+Two implementations:
+  PeerExchange     ranks of ONE box (NCCL group, NVLink / NVSwitch): every rank owns an exchange buffer that its
+                   peers map through CUDA IPC; an exchange is two kernels and nothing else - yh_map_exchange stores
+                   the rank's records, their count and its GT counts into every peer's buffer and releases a flag;
+                   the reduce kernel (yh_map_reduce_exchanged) waits on the flags inside the kernel.  No NCCL call,
+                   no host synchronisation, no size exchange on the host: torch.distributed is used once, to swap
+                   the IPC handles.
+  gather_records   anything else (gloo, several hosts, YH_DIST_P2P=0): padded all-gathers through
+                   torch.distributed, sizes through the host."""
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
 
-def world_size():
-    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+def world_size(group=None):
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 
 
-def rank():
-    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+def rank(group=None):
+    return dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
 
 
 def shard_range(n, r=None, w=None):
@@ -35,176 +36,156 @@ def shard_range(n, r=None, w=None):
     return (n * r) // w, (n * (r + 1)) // w
 
 
-def _comm_device(t):
+def _comm_device(t, group=None):
     """gloo moves CPU tensors, NCCL moves CUDA tensors."""
-    if dist.get_backend() == "gloo":
+    if dist.get_backend(group) == "gloo":
         return torch.device("cpu")
     return t.device
 
 
-def gather_records(keys, tp, gt_per_class, group=None):
-    """(keys int64 (n_r,), tp uint8 (n_r,), gt_per_class int32 (C,)) of this rank ->
-    the rank-ordered concatenation over all ranks and the summed GT counts, on every rank."""
+def gather_records(rec, gt_per_class, group=None):
+    """(rec int64 (n_r,), gt_per_class int32 (C,)) of this rank -> the rank-ordered concatenation over all ranks
+    and the summed GT counts, on every rank.  Collective; synchronises the host (sizes travel through it)."""
     w = dist.get_world_size(group)
-    home = keys.device
-    cd = _comm_device(keys)
-    n_local = torch.tensor([keys.shape[0]], dtype=torch.int64, device=cd)
+    home = rec.device
+    cd = _comm_device(rec, group)
+    n_local = torch.tensor([rec.shape[0]], dtype=torch.int64, device=cd)
     sizes = [torch.zeros_like(n_local) for _ in range(w)]
     dist.all_gather(sizes, n_local, group=group)
     sizes = [int(s.item()) for s in sizes]
     n_max = max(max(sizes), 1)
-    # one padded buffer per record field; key and flag travel as int64 / uint8
-    k_pad = torch.zeros((n_max,), dtype=torch.int64, device=cd)
-    t_pad = torch.zeros((n_max,), dtype=torch.uint8, device=cd)
-    k_pad[:keys.shape[0]] = keys.to(cd)
-    t_pad[:tp.shape[0]] = tp.to(cd)
-    k_all = [torch.empty_like(k_pad) for _ in range(w)]
-    t_all = [torch.empty_like(t_pad) for _ in range(w)]
-    dist.all_gather(k_all, k_pad, group=group)
-    dist.all_gather(t_all, t_pad, group=group)
+    r_pad = torch.zeros((n_max,), dtype=torch.int64, device=cd)
+    r_pad[:rec.shape[0]] = rec.to(cd)
+    r_all = [torch.empty_like(r_pad) for _ in range(w)]
+    dist.all_gather(r_all, r_pad, group=group)
     g = gt_per_class.to(cd).clone()
     dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
-    keys_cat = torch.cat([k_all[r][:sizes[r]] for r in range(w)]).to(home)
-    tp_cat = torch.cat([t_all[r][:sizes[r]] for r in range(w)]).to(home)
-    return keys_cat, tp_cat, g.to(home)
-
-
-class _DeviceArray:
-    """Zero-copy torch view of a raw device range (buffers come from yh_ipc_alloc, not from torch's allocator)."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    rec_cat = torch.cat([r_all[r][:sizes[r]] for r in range(w)]).to(home)
+    return rec_cat, g.to(home)
 
 
 class PeerExchange:
-    """Record buffers of this rank, mapped by every peer of the box (CUDA IPC), plus the peers' buffers mapped here.
-    All methods are collective over `group`.  See the module docstring for the protocol."""
+    """This rank's exchange buffer, mapped by every peer of the box (CUDA IPC), plus the peers' buffers mapped here.
+    Construction and close() are collective over `group`; exchange_reduce() must be called by every rank the same
+    number of times (it is what MeanAveragePrecision(sharded=True).result() does) but involves no host-side
+    collective.  `capacity` = records per rank the buffers hold; a shard that outgrows it makes every rank's result
+    NaN (and exchange_reduce raises on the rank that can tell)."""
 
-    def __init__(self, device, capacity=1 << 18, group=None):
+    def __init__(self, device, num_classes, capacity, group=None):
         import ctypes as C
         from . import _lib
         self._C, self._lib, self.L = C, _lib, _lib.lib()
         self.group, self.device = group, torch.device(device)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.capacity = 0
-        self.keys = [None] * self.world        # device addresses, index = rank
-        self.tp = [None] * self.world
-        self._alloc(int(capacity))
+        self.num_classes, self.capacity = int(num_classes), int(capacity)
+        self.epoch = 0
+        self.bufs = [None] * self.world          # device addresses of every rank's exchange buffer, index = rank
+        self._alloc()
+        total = self.world * self.capacity
+        nbytes = int(self.L.yh_workspace_bytes(_lib.YH_OP_MAP_REDUCE, total, 0, 0, self.num_classes))
+        self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        self.err = torch.zeros((1,), dtype=torch.int32, device=self.device)
 
-    # -- buffers ------------------------------------------------------------------------------
-    def _release(self):
-        C, L = self._C, self.L
-        torch.cuda.synchronize(self.device)
-        for r in range(self.world):
-            if r != self.rank:
-                for arr in (self.keys, self.tp):
-                    if arr[r]:
-                        self._lib.check(L.yh_ipc_close(C.c_void_p(arr[r])), "ipc_close")
-                        arr[r] = None
-        if self.capacity:
-            dist.barrier(group=self.group)               # every peer unmapped before the owner frees
-            for arr in (self.keys, self.tp):
-                if arr[self.rank]:
-                    self._lib.check(L.yh_ipc_free(C.c_void_p(arr[self.rank])), "ipc_free")
-                    arr[self.rank] = None
-        self.capacity = 0
-
-    def _alloc(self, capacity):
+    def _alloc(self):
         """Collective; raises the same RuntimeError on EVERY rank if any rank could not allocate or map."""
         C, L = self._C, self.L
-        self._release()
-        hk = (C.c_ubyte * self._lib.YH_IPC_HANDLE_BYTES)()
-        ht = (C.c_ubyte * self._lib.YH_IPC_HANDLE_BYTES)()
-        pk, pt = C.c_void_p(), C.c_void_p()
+        nbytes = int(L.yh_map_exchange_bytes(self.world, self.num_classes, self.capacity))
+        h = (C.c_ubyte * self._lib.YH_IPC_HANDLE_BYTES)()
+        p = C.c_void_p()
         err = None
         with torch.cuda.device(self.device):
             try:
-                self._lib.check(L.yh_ipc_alloc(capacity * 8, C.byref(pk), hk), "ipc_alloc")
-                self._lib.check(L.yh_ipc_alloc(capacity, C.byref(pt), ht), "ipc_alloc")
+                self._lib.check(L.yh_ipc_alloc(nbytes, C.byref(p), h), "ipc_alloc")       # zero-filled
             except (RuntimeError, ValueError) as e:
                 err = str(e)
-            self.keys[self.rank], self.tp[self.rank] = pk.value, pt.value
-            self.capacity = capacity
+            self.bufs[self.rank] = p.value
             handles = [None] * self.world
-            dist.all_gather_object(handles, (err, bytes(hk), bytes(ht)), group=self.group)
-            if all(h[0] is None for h in handles):
+            dist.all_gather_object(handles, (err, bytes(h)), group=self.group)
+            if all(x[0] is None for x in handles):
                 try:
                     for r in range(self.world):
                         if r == self.rank:
                             continue
-                        for arr, h in ((self.keys, handles[r][1]), (self.tp, handles[r][2])):
-                            q = C.c_void_p()
-                            self._lib.check(L.yh_ipc_open((C.c_ubyte * len(h)).from_buffer_copy(h), C.byref(q)), "ipc_open")
-                            arr[r] = q.value
+                        q = C.c_void_p()
+                        hb = handles[r][1]
+                        self._lib.check(L.yh_ipc_open((C.c_ubyte * len(hb)).from_buffer_copy(hb), C.byref(q)), "ipc_open")
+                        self.bufs[r] = q.value
                 except (RuntimeError, ValueError) as e:
                     err = str(e)
-            flag = torch.tensor([0 if (err or any(h[0] for h in handles)) else 1], dtype=torch.int32, device=self.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        if int(flag.item()) == 0:
-            self._release()
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None and all(x[0] is None for x in handles), group=self.group)
+        if not all(oks):
+            self.close()
             raise RuntimeError(f"PeerExchange: a rank could not allocate or map the exchange buffers ({err or 'peer failure'})")
 
     def close(self):
-        self._release()
+        """Collective: unmap the peers' buffers, then free the own one."""
+        C, L = self._C, self.L
+        torch.cuda.synchronize(self.device)
+        for r in range(self.world):
+            if r != self.rank and self.bufs[r]:
+                self._lib.check(L.yh_ipc_close(C.c_void_p(self.bufs[r])), "ipc_close")
+                self.bufs[r] = None
+        if self.bufs[self.rank]:
+            dist.barrier(group=self.group)               # every peer unmapped before the owner frees
+            self._lib.check(L.yh_ipc_free(C.c_void_p(self.bufs[self.rank])), "ipc_free")
+            self.bufs[self.rank] = None
 
-    # -- stage 1 + exchange -------------------------------------------------------------------
-    def match_gather(self, true_rows, pred_rows, num_classes, iou_threshold=0.5):
-        """This rank's rows -> (keys int64, tp uint8, gt_per_class int32) of ALL ranks in rank order, on every rank.
-        The returned key / flag tensors are views of this rank's exchange buffers, valid until the next call."""
+    def exchange_reduce(self, rec, nrec_dev, gt_per_class, n_hint=0):
+        """This rank's records (int64 tensor, the first *nrec_dev of it, or all of it) and GT counts ->
+        (global mAP 0-d tensor, AP per class) on every rank.  Two kernel launches, asynchronous."""
         C, L = self._C, self.L
         from ._tensor import stream_ptr
         dev = self.device
-        t, p = true_rows.contiguous(), pred_rows.contiguous()
-        n_local = torch.tensor([p.shape[0]], dtype=torch.int64, device=dev)
-        sizes = [torch.zeros_like(n_local) for _ in range(self.world)]
-        # also the fence between the previous call's readers and this call's writers (stream-ordered on every rank)
-        dist.all_gather(sizes, n_local, group=self.group)
-        sizes = [int(x.item()) for x in sizes]
-        total, offset = sum(sizes), sum(sizes[:self.rank])
-        if total > self.capacity:                       # the same decision on every rank
-            cap = self.capacity
-            while cap < total:
-                cap *= 2
-            self._alloc(cap)
-        gt = torch.empty((num_classes,), dtype=torch.int32, device=dev)
-        ka = (C.c_void_p * self.world)(*self.keys)
-        ta = (C.c_void_p * self.world)(*self.tp)
+        n_max = int(rec.shape[0])
+        if nrec_dev is None and n_max > self.capacity:
+            raise RuntimeError(f"PeerExchange: {n_max} records exceed the exchange capacity of {self.capacity} per rank; "
+                               "create the evaluator / exchange with a larger capacity")
+        self.epoch += 1
+        ap = torch.empty((self.num_classes,), dtype=torch.float32, device=dev)
+        m = torch.empty((1,), dtype=torch.float32, device=dev)
+        ba = (C.c_void_p * self.world)(*self.bufs)
         with torch.cuda.device(dev):
-            self._lib.check(L.yh_map_match_peers(self.world, self.rank, t.data_ptr(), int(t.shape[0]), p.data_ptr(),
-                                                 int(p.shape[0]), int(num_classes), float(iou_threshold), ka, ta, offset,
-                                                 None, gt.data_ptr(), stream_ptr(dev)), "map_match_peers")
-        # sums the GT counts; completes on a rank only after every peer's contribution, which follows that peer's
-        # match kernel in stream order - so all records are in this rank's buffers when stage 2 starts
-        dist.all_reduce(gt, op=dist.ReduceOp.SUM, group=self.group)
-        if total == 0:
-            return (torch.empty((0,), dtype=torch.int64, device=dev), torch.empty((0,), dtype=torch.uint8, device=dev), gt)
-        keys = torch.as_tensor(_DeviceArray(self.keys[self.rank], total, "<i8"), device=dev)
-        tp = torch.as_tensor(_DeviceArray(self.tp[self.rank], total, "|u1"), device=dev)
-        return keys, tp, gt
+            sp = stream_ptr(dev)
+            self._lib.check(L.yh_map_exchange(self.world, self.rank, ba, self.num_classes, self.capacity, rec.data_ptr(), n_max,
+                                              nrec_dev.data_ptr() if nrec_dev is not None else None, gt_per_class.data_ptr(),
+                                              self.epoch, sp), "map_exchange")
+            self._lib.check(L.yh_map_reduce_exchanged(self.world, C.c_void_p(self.bufs[self.rank]), self.num_classes,
+                                                      self.capacity, self.epoch, int(n_hint) * self.world, ap.data_ptr(),
+                                                      m.data_ptr(), self.err.data_ptr(), self.ws.data_ptr(), int(self.ws.numel()),
+                                                      sp), "map_reduce_exchanged")
+        return m[0], ap
+
+    def error(self):
+        """Host check (synchronises): 0, or YH_MAP_ERR_TIMEOUT / YH_MAP_ERR_OVERFLOW of a failed exchange."""
+        return int(self.err.item())
 
 
 _EXCHANGES = {}
 
 
-def peer_exchange(device, group=None):
-    """The cached PeerExchange of (group, device), or None when the exchange has to stay on the padded all-gathers:
-    CPU / gloo, YH_DIST_P2P=0, ranks on several hosts, more peers than the kernel takes, or IPC mapping refused."""
+def peer_exchange(device, num_classes, n_bound, group=None, capacity=None):
+    """The cached PeerExchange of (group, device, classes), created collectively on first use, or None when the
+    exchange has to stay on the padded all-gathers: CPU / gloo, YH_DIST_P2P=0, ranks on several hosts, more peers
+    than the kernels take, or IPC mapping refused.  Capacity (records per rank): `capacity` if given, else four times
+    the largest n_bound over the ranks at creation, at least 65,536."""
     import os
     import socket
     device = torch.device(device)
-    key = (id(group), device.index)
+    key = (id(group), device.index, int(num_classes))
     if key in _EXCHANGES:
         return _EXCHANGES[key]
     ex = None
     ok = (device.type == "cuda" and dist.get_backend(group) == "nccl" and os.environ.get("YH_DIST_P2P", "1") != "0"
           and dist.get_world_size(group) <= 16)
     if ok:
-        hosts = [None] * dist.get_world_size(group)
+        info = [None] * dist.get_world_size(group)
         with torch.cuda.device(device):
-            dist.all_gather_object(hosts, socket.gethostname(), group=group)
-        if len(set(hosts)) == 1:
+            dist.all_gather_object(info, (socket.gethostname(), int(capacity) if capacity else 4 * int(n_bound)), group=group)
+        if len({h for h, _ in info}) == 1:
+            cap = max(max(c for _, c in info), 1 << 16)
             try:
-                ex = PeerExchange(device, group=group)      # fails on every rank or on none
+                ex = PeerExchange(device, num_classes, cap, group=group)      # fails on every rank or on none
             except RuntimeError:
                 ex = None
     _EXCHANGES[key] = ex

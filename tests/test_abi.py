@@ -40,13 +40,22 @@ def test_argument_errors_need_no_gpu():
     assert L.yh_nms(None, 1, 300, 0.5, 0.4, None, None, None, None) == _lib.YH_ERR_UNSUPPORTED
     assert L.yh_loss(None, None, 10, 2, 20, 5.0, 0.5, None, None, None) == _lib.YH_ERR_ARG
     assert L.yh_comm_init_all(0, None, None) == _lib.YH_ERR_ARG
-    assert L.yh_map_allgather(None, None, None, None, None, 20, None, None, 0, None) == _lib.YH_ERR_ARG
+    assert L.yh_map_allgather(None, None, None, None, 20, None, 0, None) == _lib.YH_ERR_ARG
     assert L.yh_comm_destroy(None) == _lib.YH_OK
     assert L.yh_comm_p2p(None) == 0 and L.yh_comm_barrier(None, None) == _lib.YH_ERR_ARG
-    assert L.yh_map_match_p2p(None, 0, None, 0, None, 0, 20, 0.5, None, None, 0, None, None) == _lib.YH_ERR_ARG
-    assert L.yh_map_match_peers(0, 0, None, 0, None, 0, 20, 0.5, None, None, 0, None, None, None) == _lib.YH_ERR_ARG
-    assert L.yh_map_match_peers(17, 0, None, 0, None, 0, 20, 0.5, None, None, 0, None, None, None) == _lib.YH_ERR_ARG
+    assert L.yh_map_exchange(0, 0, None, 20, 0, None, 0, None, None, 1, None) == _lib.YH_ERR_ARG
+    assert L.yh_map_exchange(17, 0, None, 20, 0, None, 0, None, None, 1, None) == _lib.YH_ERR_ARG
     assert b"at most 16 peers" in L.yh_last_error()
+    assert L.yh_map_exchange(2, 0, None, 20, 0, None, 0, None, None, 0, None) == _lib.YH_ERR_ARG          # epochs start at 1
+    assert L.yh_map_reduce_exchanged(2, None, 20, 1024, 1, 0, None, None, None, None, 0, None) == _lib.YH_ERR_ARG
+    assert L.yh_map_exchange_bytes(0, 20, 1024) == 0 and L.yh_map_exchange_bytes(8, 20, 1 << 16) > 8 * 2 * 8 * (1 << 16)
+    assert L.yh_map_match(None, -1, None, None, 0, None, 20, 0.5, 0, None, None, None, 0, None) == _lib.YH_ERR_ARG
+    assert L.yh_map_match(None, 0, None, None, 0, None, 5000, 0.5, 0, None, None, None, 0, None) == _lib.YH_ERR_ARG   # C limit
+    assert L.yh_map_reduce(None, 0, None, 0, None, 20, None, None, None, 0, None) == _lib.YH_ERR_ARG
+    assert L.yh_eval_update(None, None, None, None, 4, 300, 0, 20, 0.5, None, 0, None, 0, None, None, None, None) == _lib.YH_ERR_ARG
+    assert L.yh_eval_update(None, None, None, None, 4, 49, 0, 20, 0.5, None, 0, None, 0, None, None, None, None) == _lib.YH_ERR_ARG
+    assert L.yh_workspace_bytes(_lib.YH_OP_MAP_REDUCE, 100000, 0, 0, 20) >= 2 * 8 * 100000
+    assert L.yh_workspace_bytes(_lib.YH_OP_MAP_MATCH, 100000, 0, 0, 20) >= 12 * 100000
     assert L.yh_ipc_alloc(0, None, None) == _lib.YH_ERR_ARG and L.yh_ipc_open(None, None) == _lib.YH_ERR_ARG
     assert L.yh_ipc_close(None) == _lib.YH_OK and L.yh_ipc_free(None) == _lib.YH_OK
     assert L.yh_decode_nms_host_typed(None, 9, 4, 7, 2, 20, 0.5, 0.4, None, None, None, 0) == _lib.YH_ERR_ARG

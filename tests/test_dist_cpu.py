@@ -30,11 +30,10 @@ def _worker(rank, world, port, out_dir):
     lo, hi = yd.shard_range(n)
     # ragged shards: rank r contributes r*3 + 2 records; one rank may be empty in the second round
     for rnd, cnt in enumerate((rank * 3 + 2, 0 if rank == 0 else 4)):
-        keys = torch.arange(cnt, dtype=torch.int64) + 1000 * (rank + 1) + 100 * rnd
-        tp = (torch.arange(cnt) % 2).to(torch.uint8)
+        rec = ((torch.arange(cnt, dtype=torch.int64) + 1000 * (rank + 1) + 100 * rnd) << 1) | (torch.arange(cnt) % 2)
         gt = torch.tensor([rank + 1, 10 * (rank + 1), 0], dtype=torch.int32)
-        k, t, g = yd.gather_records(keys, tp, gt)
-        np.savez(os.path.join(out_dir, f"r{rank}_{rnd}.npz"), k=k.numpy(), t=t.numpy(), g=g.numpy(), lo=lo, hi=hi)
+        k, g = yd.gather_records(rec, gt)
+        np.savez(os.path.join(out_dir, f"r{rank}_{rnd}.npz"), k=k.numpy(), g=g.numpy(), lo=lo, hi=hi)
     dist.destroy_process_group()
 
 
@@ -43,11 +42,10 @@ def test_gather_records_world2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for rnd, counts in enumerate(((2, 5), (0, 4))):
-        want_k = np.concatenate([np.arange(c) + 1000 * (r + 1) + 100 * rnd for r, c in enumerate(counts)])
-        want_t = np.concatenate([np.arange(c) % 2 for c in counts]).astype(np.uint8)
+        want_k = np.concatenate([((np.arange(c) + 1000 * (r + 1) + 100 * rnd) << 1) | (np.arange(c) % 2) for r, c in enumerate(counts)])
         for r in range(world):
             z = np.load(tmp_path / f"r{r}_{rnd}.npz")
-            assert np.array_equal(z["k"], want_k) and np.array_equal(z["t"], want_t)
+            assert np.array_equal(z["k"], want_k)
             assert np.array_equal(z["g"], [3, 30, 0])
     z0, z1 = np.load(tmp_path / "r0_0.npz"), np.load(tmp_path / "r1_0.npz")
     assert (int(z0["lo"]), int(z0["hi"]), int(z1["lo"]), int(z1["hi"])) == (0, 5, 5, 11)

@@ -402,16 +402,17 @@ def test_sharded_map_single_process_emulation(dev):
     ev = yu.MeanAveragePrecision(20, 2)
     ev.update_state(_cuda(yt, dev), _cuda(mp, dev))
     whole = float(ev.result())
-    ks, ts, gs = [], [], 0
     for w in (3, 8):
-        ks, ts, gs = [], [], 0
+        rs, gs = [], 0
         for r in range(w):
             lo, hi = 400 * r // w, 400 * (r + 1) // w
             e = yu.MeanAveragePrecision(20, 2)
             e.update_state(_cuda(yt[lo:hi], dev), _cuda(mp[lo:hi], dev))
-            k, t, g = yu.map_match(e.all_true_boxes_variable, e.all_pred_boxes_variable, 20, 0.5)
-            ks.append(k); ts.append(t); gs = gs + g
-        m, _ = yu.map_reduce(torch.cat(ks), torch.cat(ts), gs, 20)
+            # the general path (arbitrary rows) on the shard's rows == the records the evaluator kept while updating
+            rec, g = yu.map_match(e.all_true_boxes_variable, e.all_pred_boxes_variable, 20, 0.5)
+            assert torch.equal(rec, e._st["rec"][:rec.shape[0]]) and torch.equal(g, e._st["gt"])
+            rs.append(rec); gs = gs + g
+        m, _ = yu.map_reduce(torch.cat(rs), gs, 20)
         assert float(m) == whole
 
 
