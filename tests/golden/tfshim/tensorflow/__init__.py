@@ -89,6 +89,9 @@ class Tensor(np.ndarray):
     def numpy(self):
         return np.asarray(self)
 
+    def set_shape(self, shape):   # static shape hints are no-ops on concrete values
+        return None
+
     def __bool__(self):           # TF: a single-element predicate is squeezed to a scalar by cond
         if self.size != 1:
             raise ValueError("truth value of a multi-element tensor")
@@ -228,7 +231,20 @@ def print(*_a, **_k):  # noqa: A001 - tf.print: the reference's progress chatter
 
 def py_function(func, inp, Tout):
     out = func(*[np.asarray(_val(v)) for v in inp])
+    if isinstance(Tout, (list, tuple)):
+        return [cast(o, t) for o, t in zip(out, Tout)]
     return cast(out, Tout)
+
+
+def custom_gradient(f):
+    """tf.custom_gradient, eager: f(*args) -> (y, grad_fn).  There is no tape here; the backward function is kept on
+    the result as `y._grad_fn` so that a test can apply it to an upstream gradient, which is all a tape would do."""
+    def wrapper(*args):
+        y, grad_fn = f(*args)
+        y = _t(_val(y))
+        y._grad_fn = grad_fn
+        return y
+    return wrapper
 
 
 # ---------------------------------------------------------------- shape / structure ops
@@ -484,5 +500,25 @@ class _DenseHashTable:
 lookup = types.ModuleType("tensorflow.lookup")
 lookup.experimental = types.ModuleType("tensorflow.lookup.experimental")
 lookup.experimental.DenseHashTable = _DenseHashTable
+
+# ---------------------------------------------------------------- tf.experimental.dlpack
+# Stand-in for "a TF tensor living on the GPU": to_dlpack puts the values on the current CUDA device (through torch, when
+# there is one - on a CPU-only box the capsule is a CPU tensor, which libyolohot rejects) and hands out the DLPack capsule;
+# from_dlpack brings a capsule's values back as a Tensor.
+def _to_dlpack(x):
+    t = _torch.from_numpy(np.ascontiguousarray(np.asarray(_val(x))))
+    if _torch.cuda.is_available():
+        t = t.cuda()
+    return _torch.utils.dlpack.to_dlpack(t)
+
+
+def _from_dlpack(capsule):
+    return _t(_torch.utils.dlpack.from_dlpack(capsule).detach().cpu().numpy())
+
+
+experimental = types.ModuleType("tensorflow.experimental")
+experimental.dlpack = types.ModuleType("tensorflow.experimental.dlpack")
+experimental.dlpack.to_dlpack = _to_dlpack
+experimental.dlpack.from_dlpack = _from_dlpack
 
 from . import keras  # noqa: E402,F401  (tensorflow.keras.losses.Loss)

@@ -227,3 +227,33 @@ def test_numpy_evaluator_overwrites_after_reset(dev):
     e2.update_state(yt[20:], yp[20:])
     assert first > 0 and np.array_equal(en.all_pred_boxes_variable, e2.all_pred_boxes_variable)
     assert float(en.result()) == float(e2.result())
+
+
+def test_tf_keras_loss_branch_end_to_end(dev):
+    """loss.py:100-118 + yolo_v1.py:810,829: the Keras-loss form of YoloV1Loss (tf.custom_gradient over yh_loss_dl,
+    tensors through DLPack) gives the torch path's value and gradient.  Runs against the TensorFlow stand-in of
+    tests/golden/tfshim in its own process (TensorFlow itself is not in this image)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "tf_branch_check.py"), "gpu"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "tf_branch_check ok (gpu)" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_half_precision_head_trains_through_the_loss(dev):
+    """A bf16 / fp16 head output that requires grad keeps its autograd graph through YoloV1Loss."""
+    from yolohot import loss as yl
+    yt = F.synth_labels(8, seed=7)
+    yp = F.synth_loss_pred(yt.shape, seed=7)
+    t = torch.from_numpy(yt).to(dev)
+    for dt in (torch.bfloat16, torch.float16):
+        w = torch.from_numpy(yp).to(dev).to(dt).requires_grad_(True)         # "the model's parameters"
+        head = w * 1.0                                                       # a non-leaf half-precision head output
+        total = yl.YoloV1Loss(20, 2)(t, head)
+        total.backward()
+        ref = w.detach().float().requires_grad_(True)
+        yl.YoloV1Loss(20, 2)(t, ref).backward()
+        assert w.grad is not None and w.grad.dtype == dt
+        assert torch.equal(w.grad, ref.grad.to(dt))

@@ -55,3 +55,16 @@ def test_product_path_fails_loudly_without_a_gpu():
                  lambda: yu.MeanAveragePrecision(20, 2).update_state(p, p)):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             call()
+
+
+def test_tf_keras_branch_of_the_loss_is_taken_and_needs_a_gpu():
+    """With `tensorflow` importable (the stand-in), YoloV1Loss is a keras.losses.Loss and its call goes through
+    tf.custom_gradient + DLPack; without a CUDA device it must refuse, not fall back.  Own process: the stand-in
+    must not leak into the other tests."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "tf_branch_check.py"), "cpu"], capture_output=True, text=True,
+                       timeout=300, env=env)
+    assert r.returncode == 0 and "tf_branch_check ok (cpu)" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
