@@ -359,12 +359,13 @@ class MeanAveragePrecision:
         st = self._st
         if st is None or st["dev"] != dev:
             cap = max(4096, 2 * extra)
+            # the two row cursors and the per-class GT counts share one tensor: a restart is ONE fill launch
+            state = torch.zeros((2 + (self._num_classes + 1) // 2,), dtype=torch.int64, device=dev)
             st = {"dev": dev, "cap": cap, "bound": 0,
                   "pred": torch.empty((cap, 7), dtype=torch.float32, device=dev),
                   "true": torch.empty((cap, 7), dtype=torch.float32, device=dev),
                   "rec": torch.empty((cap,), dtype=torch.int64, device=dev),
-                  "cursors": torch.zeros((2,), dtype=torch.int64, device=dev),
-                  "gt": torch.zeros((self._num_classes,), dtype=torch.int32, device=dev)}
+                  "state": state, "cursors": state[:2], "gt": state[2:].view(torch.int32)[:self._num_classes]}
             self._st = st
         if st["bound"] + extra > st["cap"]:
             cap = max(2 * st["cap"], st["bound"] + 2 * extra)
@@ -407,8 +408,7 @@ class MeanAveragePrecision:
         M = S * S
         st = self._ensure(dev, n * M)
         if self.img_idx == 0:                       # utils.py:484-486: first image overwrites
-            st["cursors"].zero_()
-            st["gt"].zero_()
+            st["state"].zero_()
             st["bound"] = 0
         key = (n, M)
         bufs = self._cache.get(key)

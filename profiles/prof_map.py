@@ -1,5 +1,7 @@
-"""mAP pipeline at scale: evaluator update (decode+NMS of y_true and y_pred, row append) and result
-(match + reduce) for YH_PROF_IMAGES images: python profiles/prof_map.py"""
+"""mAP pipeline: python profiles/prof_map.py [cfg4|big]
+cfg4: BASELINE configs[3] - 5,000 images through MeanAveragePrecision.update_state + result(), 10 passes
+      (4 launches per pass: decode+NMS x2, yh_eval_update, yh_map_reduce; no host synchronisation);
+big:  YH_PROF_IMAGES images (default 1,000,000) accumulated in 50k-image batches, then result() alone."""
 import os
 import sys
 import time
@@ -10,30 +12,49 @@ sys.path.insert(0, os.path.join(ROOT, "keras-object-detection_b200"))
 import torch  # noqa: E402
 
 from tests import fixtures as F  # noqa: E402
-from yolohot import utils as yu  # noqa: E402
+from yolohot import launch_count, utils as yu  # noqa: E402
 
 dev = torch.device("cuda:0")
-n = int(os.environ.get("YH_PROF_IMAGES", 100_000))
-base = 5000
-yt0 = F.synth_labels(base, seed=11)
-yp0 = F.synth_map_pred(yt0)
-reps = (n + base - 1) // base
-yt = torch.from_numpy(yt0).to(dev).repeat(reps, 1, 1, 1)[:n].contiguous()
-yp = torch.from_numpy(yp0).to(dev).repeat(reps, 1, 1, 1)[:n].contiguous()
+mode = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
+if mode == "cfg4":
+    yt0 = F.synth_labels(5000, seed=11)
+    a, b = torch.from_numpy(yt0).to(dev), torch.from_numpy(F.synth_map_pred(yt0)).to(dev)
+    ev = yu.MeanAveragePrecision(20, 2)
 
-
-def run():
+    def one():
+        ev.reset_states()
+        ev.update_state(a, b)
+        return ev.result()
+    for _ in range(3):
+        m = one()
+    torch.cuda.synchronize()
+    l0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(10):
+        m = one()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"cfg4: update_state + result() {1e3 * (time.perf_counter() - t0) / 10:.4f} ms wall, {e0.elapsed_time(e1) / 10:.4f} ms on the device, "
+          f"{(launch_count() - l0) / 10:.1f} launches per pass, mAP {float(m):.6f}, {int(ev._st['cursors'][0])} records")
+else:
+    n = int(os.environ.get("YH_PROF_IMAGES", 1_000_000))
+    yt0 = F.synth_labels(50_000, seed=11)
+    a, b = torch.from_numpy(yt0).to(dev), torch.from_numpy(F.synth_map_pred(yt0)).to(dev)
     ev = yu.MeanAveragePrecision(20, 2)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    for lo in range(0, n, 65536):
-        ev.update_state(yt[lo:lo + 65536], yp[lo:lo + 65536])
+    for lo in range(0, n, 50_000):
+        k = min(50_000, n - lo)
+        ev.update_state(a[:k], b[:k])
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    m = float(ev.result())
-    torch.cuda.synchronize(); t2 = time.perf_counter()
-    return t1 - t0, t2 - t1, m, ev.all_pred_boxes_variable.shape[0], ev.all_true_boxes_variable.shape[0]
-
-
-run()
-u, r, m, npred, ngt = run()
-print(f"{n} images: update_state {u * 1e3:.2f} ms, result {r * 1e3:.2f} ms, mAP {m:.6f}, {npred} detections, {ngt} ground truths; "
-      f"{n / (u + r) / 1e6:.2f} M images/s end to end, result stage {28 * (npred + ngt) / r / 1e9:.1f} GB/s of rows")
+    ev.result()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); m = ev.result(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    nrec = int(ev._st["cursors"][0])
+    print(f"big: {n} images, update_state total {1e3 * (t1 - t0):.2f} ms ({n / (t1 - t0) / 1e6:.1f} M images/s), result() {min(ts):.3f} ms "
+          f"(min of 5) over {nrec} records = {8 * nrec * 3 * 5 / (min(ts) * 1e-3) / 1e9:.0f} GB/s of sort traffic (3 x 8 B x 5 passes), mAP {float(m):.6f}")
