@@ -195,7 +195,7 @@ extern "C" int yh_decode(const float *pred, int64_t n, int S, int B, int C, floa
     cfg.S = S; cfg.B = B; cfg.C = C; cfg.M = S * S; cfg.D = C + 5 * B;
     cfg.inv_s = static_cast<float>(1.0 / static_cast<double>(S));
     cfg.iou_thr = cfg.conf_thr = 0.f; cfg.ws_bytes = 0; cfg.tbl_rows = 0;
-    cfg.thr_fast = 0; cfg.score_mode = 0;
+    cfg.thr_fast = 0; cfg.band = INFINITY; cfg.score_mode = 0;
     if (n == 0) return YH_OK;
     YH_REQUIRE(pred && out_boxes, "decode: null pointer");
     YH_REQUIRE(reinterpret_cast<uintptr_t>(out_boxes) % 8 == 0, "decode: out_boxes must be 8-byte aligned");

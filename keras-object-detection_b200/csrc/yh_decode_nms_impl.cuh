@@ -37,6 +37,7 @@ struct NmsCfg {
     float inv_s;             // float32(1 / S)                         (utils.py:207)
     float iou_thr, conf_thr;
     int thr_fast;            // iou_thr is a positive normal float: the division-free filter of suppresses() applies
+    float band;              // 2^-20 when it does, +inf when the division must always decide
     int score_mode;          // 0 = reference (best box confidence); 1 = confidence x class probability (extension)
     int ws_bytes;            // per-warp workspace bytes
     int tbl_rows;            // rows of the class table (C for fused, 32*NS for row input)
@@ -101,7 +102,21 @@ struct WarpWs {
 // fl(inter / den) < thr.  Inside the band (probability ~1e-6 per test on continuous data), for
 // den <= 0 (degenerate negative-extent boxes), NaN/inf operands or an unusual thr, the reference's
 // own division decides.
-__device__ __forceinline__ bool suppresses(const float4 &pc, float pa, const float4 &qc, float qa, const NmsCfg &cfg)
+//
+// den > 0 needs no test of its own: both areas are absolute values, the clipped extents of the intersection are no
+// larger than either box's own (so inter <= min(a1, a2), and inter = 0 as soon as a box has a negative extent), hence
+// den >= 1e-6 for finite operands; a NaN or infinite den makes p and d NaN / infinite and the comparison below false.
+// cfg.band is 2^-20 when the filter applies and +inf otherwise (YH_EXACT_DIV=1, unusual thr): `|d| > |p| * inf` is false
+// (|p| * inf is +inf, or NaN for p = 0).
+// The common path is straight-line code (one rarely taken branch to the division).
+static __device__ __noinline__ unsigned suppresses_exact(float inter, float den, float thr)   // out of line: taken ~1e-6 of the time
+{
+    float v = 0.0f;                                          // a zero intersection gives IoU = +0 exactly
+    if (inter != 0.0f) v = __fdiv_rn(inter, den);
+    return (v < thr) ? 0u : 1u;                              // utils.py:108 keeps iff iou < thr
+}
+
+__device__ __forceinline__ unsigned suppresses(const float4 &pc, float pa, const float4 &qc, float qa, const NmsCfg &cfg)
 {
     const float iw = clip01(__fsub_rn(fminf(pc.y, qc.y), fmaxf(pc.x, qc.x)));
     const float ih = clip01(__fsub_rn(fminf(pc.w, qc.w), fmaxf(pc.z, qc.z)));
@@ -109,10 +124,10 @@ __device__ __forceinline__ bool suppresses(const float4 &pc, float pa, const flo
     const float den = __fadd_rn(__fsub_rn(__fadd_rn(pa, qa), inter), 1e-6f);
     const float p = __fmul_rn(cfg.iou_thr, den);
     const float d = __fsub_rn(inter, p);
-    if (cfg.thr_fast && den > 0.0f && fabsf(d) > __fmul_rn(p, 9.5367431640625e-07f)) return !(d < 0.0f);
-    float v = 0.0f;                                          // a zero intersection gives IoU = +0 exactly
-    if (inter != 0.0f) v = __fdiv_rn(inter, den);
-    return !(v < cfg.iou_thr);                               // utils.py:108 keeps iff iou < thr
+    unsigned s = (d < 0.0f) ? 0u : 1u;                       // 1 = suppresses
+    if (__builtin_expect(!(fabsf(d) > __fmul_rn(fabsf(p), cfg.band)), 0))   // inside the band, or not finite:
+        s = suppresses_exact(inter, den, cfg.iou_thr);                       // the reference's division decides
+    return s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -362,7 +377,7 @@ __device__ __forceinline__ int nms_warp(const float (&conf)[NS], const float4 (&
                     while (w) {
                         const int b = __ffs(w) - 1;
                         w &= w - 1;
-                        if (suppresses(ws.scor[32 * t2 + b], ws.sarea[32 * t2 + b], qc, qa, cfg)) supp[t][t2] |= 1u << b;
+                        supp[t][t2] |= suppresses(ws.scor[32 * t2 + b], ws.sarea[32 * t2 + b], qc, qa, cfg) << b;
                     }
                 }
             }
@@ -974,7 +989,7 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const E *__res
                     while (w) {
                         const int b = __ffs(w) - 1;
                         w &= w - 1;
-                        if (suppresses(scor[32 * w2 + b], sarea[32 * w2 + b], qc, qa, cfg)) supp[w2] |= 1u << b;
+                        supp[w2] |= suppresses(scor[32 * w2 + b], sarea[32 * w2 + b], qc, qa, cfg) << b;
                     }
                 }
             }
@@ -990,7 +1005,7 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const E *__res
                     while (w) {
                         const int b = __ffs(w) - 1;
                         w &= w - 1;
-                        if (suppresses(scor[32 * w2 + b], sarea[32 * w2 + b], qc, qa, cfg)) hs |= 1u << b;
+                        hs |= suppresses(scor[32 * w2 + b], sarea[32 * w2 + b], qc, qa, cfg) << b;
                     }
                     help[q2 * (kTeamWarpsMax / 2) + w2] = hs;
                 }
@@ -1068,6 +1083,7 @@ static void set_thr(NmsCfg &cfg)
 {
     const float t = cfg.iou_thr;
     cfg.thr_fast = (env_int("YH_EXACT_DIV", 0) == 0 && std::isfinite(t) && t > 1e-30f && t < 1e30f) ? 1 : 0;
+    cfg.band = cfg.thr_fast ? 9.5367431640625e-07f : INFINITY;
 }
 
 static int fill_cfg(NmsCfg &cfg, int S, int B, int C, float iou_thr, float conf_thr)
