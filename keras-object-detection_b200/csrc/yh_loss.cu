@@ -382,7 +382,15 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
 // deferral list, one barrier pair per 256 cells) at twice the occupancy: 350 us against 376 us for the ring kernel at
 // batch 131,072 (DRAM at 6.6 TB/s).  On the 4,096-image cfg3 batch the ring kernel keeps a small edge (22.0 vs 22.9 us).
 // ------------------------------------------------------------------------------------------
-constexpr int kGatherThreads = 256;
+#ifndef YH_GATHER_THREADS
+#define YH_GATHER_THREADS 256
+#endif
+#ifndef YH_GATHER_CPT
+#define YH_GATHER_CPT 2
+#endif
+constexpr int kGatherThreads = YH_GATHER_THREADS;
+constexpr int kGatherCPT = YH_GATHER_CPT;                       // cells per thread: fewer, fatter threads keep a cfg3-sized batch in ONE wave
+constexpr int kGatherTile = kGatherThreads * kGatherCPT;
 
 template <bool kGrad>
 __global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
@@ -390,38 +398,43 @@ __global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float
                                                                      double *__restrict__ partials, unsigned *__restrict__ ticket,
                                                                      float *__restrict__ out_terms)
 {
-    __shared__ int heavy[kGatherThreads];
-    __shared__ int wcount[kGatherThreads / 32];
+    __shared__ int heavy[kGatherTile];
+    __shared__ int wcount[kGatherCPT][kGatherThreads / 32];
     const int C = cfg.C, D = cfg.D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int nwarp = kGatherThreads / 32;
-    const int64_t n_tiles = (cfg.n_cells + kGatherThreads - 1) / kGatherThreads;
-    const bool gvec_ok = kGrad && (reinterpret_cast<uintptr_t>(grad) % 16 == 0);
+    const int64_t n_tiles = (cfg.n_cells + kGatherTile - 1) / kGatherTile;
+    const bool gvec_ok = kGrad && (reinterpret_cast<uintptr_t>(grad) % 16 == 0) && ((static_cast<int64_t>(kGatherTile) * D) % 4 == 0);
     const bool pair_ok = (((C | D) & 1) == 0) && (reinterpret_cast<uintptr_t>(yt) % 8 == 0);   // y_true[C..C+3] as two aligned pairs
     double sxy = 0, swh = 0, sob = 0, snb = 0, scl = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t cell0 = tile * kGatherThreads;
-        const int cells = static_cast<int>(min(static_cast<int64_t>(kGatherThreads), cfg.n_cells - cell0));
-        const int cell = threadIdx.x;
-        const bool in = cell < cells;
-        float obj = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, b4 = 0.f, c0 = 0.f;
-        if (in) {
-            const float *t = yt + (cell0 + cell) * D + C;
-            if (pair_ok) {
-                const float2 u = __ldg(reinterpret_cast<const float2 *>(t));
-                const float2 v = __ldg(reinterpret_cast<const float2 *>(t + 2));
-                obj = u.x; b1 = u.y; b2 = v.x; b3 = v.y;
-            } else {
-                obj = __ldg(t); b1 = __ldg(t + 1); b2 = __ldg(t + 2); b3 = __ldg(t + 3);
+        const int64_t cell0 = tile * kGatherTile;
+        const int cells = static_cast<int>(min(static_cast<int64_t>(kGatherTile), cfg.n_cells - cell0));
+        float obj[kGatherCPT], b1[kGatherCPT], b2[kGatherCPT], b3[kGatherCPT], b4[kGatherCPT], c0[kGatherCPT];
+        bool in[kGatherCPT];
+#pragma unroll
+        for (int j = 0; j < kGatherCPT; ++j) {                               // every load of the thread in flight together
+            const int cell = j * kGatherThreads + threadIdx.x;
+            in[j] = cell < cells;
+            obj[j] = b1[j] = b2[j] = b3[j] = b4[j] = c0[j] = 0.f;
+            if (in[j]) {
+                const float *t = yt + (cell0 + cell) * D + C;
+                if (pair_ok) {
+                    const float2 u = __ldg(reinterpret_cast<const float2 *>(t));
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(t + 2));
+                    obj[j] = u.x; b1[j] = u.y; b2[j] = v.x; b3[j] = v.y;
+                } else {
+                    obj[j] = __ldg(t); b1[j] = __ldg(t + 1); b2[j] = __ldg(t + 2); b3[j] = __ldg(t + 3);
+                }
+                b4[j] = __ldg(t + 4);
+                c0[j] = __ldg(yp + (cell0 + cell) * D + C);
             }
-            b4 = __ldg(t + 4);
-            c0 = __ldg(yp + (cell0 + cell) * D + C);
         }
         // ---- gradient tile := 0 while the loads are in flight (overwritten below where it is not) ----
         if (kGrad) {
             float *gg = grad + cell0 * D;
             const int nfl = cells * D;
-            if (gvec_ok && cells == kGatherThreads) {
+            if (gvec_ok && cells == kGatherTile) {
                 float4 *g4 = reinterpret_cast<float4 *>(gg);
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int i = threadIdx.x; i < (nfl >> 2); i += kGatherThreads) g4[i] = z;
@@ -430,26 +443,37 @@ __global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float
             }
         }
         // ---- pass A: light cells, compaction of the heavy ones ----
-        const bool hv = in && ((obj != 0.0f) || (b1 != 0.0f) || (b2 != 0.0f) || (b3 != 0.0f) || (b4 != 0.0f));
-        float g_light = 0.f;
-        if (in && !hv) {
-            const float noobj = __fsub_rn(1.0f, obj);                         // loss.py:163
-            const float z = __fsub_rn(0.0f, c0);                              // responsible = box 0
-            snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));    // loss.py:197
-            g_light = cfg.ln * 2.0f * noobj * c0;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, hv);
-        if (lane == 0) wcount[warp] = __popc(bal);
-        __syncthreads();                                                      // also: zero fill before the stores below
-        int base = 0, n_heavy = 0;
+        bool hv[kGatherCPT];
+        float g_light[kGatherCPT];
+        unsigned bal[kGatherCPT];
 #pragma unroll
-        for (int w = 0; w < nwarp; ++w) {
-            const int k = wcount[w];
-            base += (w < warp) ? k : 0;
-            n_heavy += k;
+        for (int j = 0; j < kGatherCPT; ++j) {
+            hv[j] = in[j] && ((obj[j] != 0.0f) || (b1[j] != 0.0f) || (b2[j] != 0.0f) || (b3[j] != 0.0f) || (b4[j] != 0.0f));
+            g_light[j] = 0.f;
+            if (in[j] && !hv[j]) {
+                const float noobj = __fsub_rn(1.0f, obj[j]);                      // loss.py:163
+                const float z = __fsub_rn(0.0f, c0[j]);                           // responsible = box 0
+                snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));    // loss.py:197
+                g_light[j] = cfg.ln * 2.0f * noobj * c0[j];
+            }
+            bal[j] = __ballot_sync(0xffffffffu, hv[j]);
+            if (lane == 0) wcount[j][warp] = __popc(bal[j]);
         }
-        if (hv) heavy[base + __popc(bal & ((1u << lane) - 1u))] = cell;
-        if (kGrad && in && !hv) grad[(cell0 + cell) * D + C] = g_light;
+        __syncthreads();                                                      // also: zero fill before the stores below
+        int n_heavy = 0;
+#pragma unroll
+        for (int j = 0; j < kGatherCPT; ++j) {
+            int base = n_heavy;
+#pragma unroll
+            for (int w = 0; w < nwarp; ++w) {
+                const int k = wcount[j][w];
+                base += (w < warp) ? k : 0;
+                n_heavy += k;
+            }
+            const int cell = j * kGatherThreads + threadIdx.x;
+            if (hv[j]) heavy[base + __popc(bal[j] & ((1u << lane) - 1u))] = cell;
+            if (kGrad && in[j] && !hv[j]) grad[(cell0 + cell) * D + C] = g_light[j];
+        }
         __syncthreads();                                                      // heavy[] complete
         // ---- pass B: box / confidence terms of the heavy cells, thread per cell; pass C: class term, warp per cell ----
         for (int h = threadIdx.x; h < n_heavy; h += kGatherThreads) {
@@ -460,7 +484,7 @@ __global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float
             const int64_t off = (cell0 + heavy[h]) * D;
             heavy_class_term<kGrad>(yt + off, yp + off, kGrad ? grad + off : nullptr, C, lane, scl);
         }
-        __syncthreads();                                                      // heavy[] / wcount[] are reused by the next tile
+        if (tile + gridDim.x < n_tiles) __syncthreads();                      // heavy[] / wcount[] are reused by the next tile
     }
     block_finish(sxy, swh, sob, snb, scl, cfg, partials, ticket, out_terms);
 }
@@ -516,12 +540,13 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
         return YH_ERR_UNSUPPORTED;
     }
     cfg.tile_cells = tile;
-    // two kernels: the TMA ring (lowest latency on a batch of a few thousand images, 22.0 vs 22.9 us on cfg3) and the
-    // gather variant (half the instructions, 352 vs 389 us on a batch of 131,072); YH_LOSS_GATHER = 0 / 1 forces one of them
+    // two kernels: the TMA ring (small batches) and the gather variant (half the instructions: 352 vs 389 us on a batch of
+    // 131,072; with two cells per thread the cfg3 batch is a single wave of CTAs: 21.0 vs 21.8 us); YH_LOSS_GATHER = 0 / 1
+    // forces one of them
     const char *gv = getenv("YH_LOSS_GATHER");                     // read per call: the tests switch it
     const int env_gather = (gv && *gv) ? atoi(gv) : -1;
-    const bool gather = env_gather >= 0 ? env_gather != 0 : n_cells >= (1 << 20);
-    const int64_t n_tiles = gather ? (n_cells + kGatherThreads - 1) / kGatherThreads : (n_cells + tile - 1) / tile;
+    const bool gather = env_gather >= 0 ? env_gather != 0 : n_cells >= (1 << 16);
+    const int64_t n_tiles = gather ? (n_cells + kGatherTile - 1) / kGatherTile : (n_cells + tile - 1) / tile;
     auto kern = gather ? (out_grad ? loss_gather_kernel<true> : loss_gather_kernel<false>)
                        : (out_grad ? loss_kernel<true> : loss_kernel<false>);
     const size_t smem = gather ? 0 : smem_tma;
