@@ -16,6 +16,13 @@
  *     channels [class probs (C) | B x (conf, x, y, w, h)]  (yolo_v1/dataset.py:88-112).
  *   - return value: YH_OK or a negative YH_ERR_*; the message is in yh_last_error()
  *     (thread-local).  No exceptions, aborts or CPU fallbacks cross this boundary.
+ *   - inputs are expected to be FINITE.  Signed zeros and infinities / NaNs in the values a
+ *     result is computed from (the selected box of a cell, its class scores, the confidences)
+ *     behave like the reference's float32 arithmetic (tests: test_ref_golden.py, "nonfinite_sel").
+ *     One documented deviation: the reference picks a cell's box by multiplying every box by
+ *     a 0/1 mask and summing (utils.py:184-197), so an inf / NaN in a box that was NOT
+ *     selected turns the cell's row into NaN there; the kernels select, and return the selected
+ *     box.  Nothing is raised for non-finite inputs.
  */
 #ifndef YOLOHOT_H_
 #define YOLOHOT_H_

@@ -110,6 +110,65 @@ def recorded_pixel_boxes(fn, img_shape, boxes, names_path):
     return np.array(rec, np.int32).reshape(-1, 4)
 
 
+# ---- the stale evaluators ------------------------------------------------------------------
+# metric.py:7 imports names that utils.py no longer defines; their bodies survive only as COMMENTED-OUT source in
+# tmp.py.  The text of those comment blocks is executed here as it stands (leading "# " stripped), on top of the
+# reference's own utils.py, and metric.py is imported unmodified against the result:
+#   get_all_bboxes              tmp.py:96-157
+#   mean_average_precision_2    tmp.py:440-595           (-> metric.MeanAveragePrecision2.result, metric.py:96-99)
+#   mean_average_precision      tmp.py:187-405, the older (true, pred, iou_threshold, num_classes) signature that
+#                               metric.MeanAveragePrecision.result (metric.py:55-56) calls with two arguments
+#   non_max_suppression_2       NO body survives anywhere; metric.py:77 calls it with the keywords of the live
+#                               utils.non_max_suppression, which is bound to the name
+#   non_max_suppression(.., threshold=)   metric.py:30 uses the keyword of tmp.py:8-89, whose sort is a
+#                               TensorArray.scatter by argsort (the inverse permutation - a bug, presumably why it was
+#                               replaced); the live function is bound behind that keyword instead
+def _tmp_block(lines, name):
+    """The commented-out top-level function `name` of tmp.py, decorator included, as source text."""
+    start = next(i for i, l in enumerate(lines) if l.startswith(f"# def {name}("))
+    if lines[start - 1].startswith("# @tf.function"):
+        start -= 1
+    end = start + 2
+    while end < len(lines) and not (lines[end].startswith("# @tf.function") or lines[end].startswith("# def ")
+                                    or lines[end].startswith("# class ")):
+        end += 1
+    body = []
+    for l in lines[start:end]:
+        body.append(l[2:] if l.startswith("# ") else (l[1:] if l.startswith("#") else l))
+    return start + 1, end, "\n".join(body) + "\n"
+
+
+def stale_metric_module(variant):
+    """metric.py imported against utils.py + the uncommented tmp.py blocks.  variant 2: MeanAveragePrecision2's
+    imports; variant 1: MeanAveragePrecision's (older mean_average_precision, `threshold=` keyword)."""
+    import importlib.util
+    lines = open(os.path.join(REF, "tmp.py")).read().split("\n")
+    u = types.ModuleType("utils")
+    u.__file__ = os.path.join(REF, "utils.py")
+    exec(compile(open(u.__file__).read(), u.__file__, "exec"), u.__dict__)
+    live_nms, live_map = u.non_max_suppression, u.mean_average_precision
+    used = {}
+    for name in ("get_all_bboxes", "mean_average_precision_2") + (("mean_average_precision",) if variant == 1 else ()):
+        lo, hi, src = _tmp_block(lines, name)
+        used[name] = (lo, hi)
+        exec(compile(src, os.path.join(REF, "tmp.py") + f":{lo}-{hi}", "exec"), u.__dict__)
+    u.non_max_suppression_2 = live_nms
+    if variant == 1:
+        u.non_max_suppression = lambda boxes, iou_threshold=0.5, threshold=0.4: live_nms(boxes, iou_threshold, threshold)
+    else:
+        u.mean_average_precision = live_map
+    saved = sys.modules.get("utils")
+    sys.modules["utils"] = u
+    try:
+        spec = importlib.util.spec_from_file_location(f"metric_v{variant}", os.path.join(REF, "metric.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    finally:
+        sys.modules["utils"] = saved
+    return m, u, used
+
+
+
 def main():
     g = {}
     # ---- the reference's own fixtures ------------------------------------------------------
@@ -195,6 +254,50 @@ def main():
     g["rows_true"], g["rows_pred"] = true_rows, pred_rows
     g["rows_map"] = np.float32(np.asarray(RU.mean_average_precision(T(true_rows), T(pred_rows), 4)))
     g["rows_map_thr03"] = np.float32(np.asarray(RU.mean_average_precision(T(true_rows), T(pred_rows), 4, iou_threshold=0.3)))
+
+    # ---- a7: the stale metric.py evaluators, executed from metric.py + the commented-out text of tmp.py -----------
+    yt, yp = g["map40_yt"], g["map40_yp"]
+    m2, u2, used = stale_metric_module(2)
+    assert used["get_all_bboxes"][0] == 96 and used["mean_average_precision_2"][0] == 440, used      # decorator lines
+    g["stale_gab"] = np.asarray(u2.get_all_bboxes(T(yp[:8])))                              # tmp.py:96-157 on 8 images
+    ev = m2.MeanAveragePrecision2()
+    ev.update_state(T(yt[:25]), T(yp[:25]))
+    ev.update_state(T(yt[25:]), T(yp[25:]))
+    g["stale2_true_rows"], g["stale2_pred_rows"] = np.asarray(ev.all_true_bboxes_variable), np.asarray(ev.all_pred_bboxes_variable)
+    g["stale2_map"] = np.float32(np.asarray(ev.result()))                                  # tmp.py:440-595
+    m1, u1, used1 = stale_metric_module(1)
+    assert used1["mean_average_precision"][0] == 187, used1
+    ev = m1.MeanAveragePrecision()
+    ev.update_state(T(yt[:25]), T(yp[:25]))
+    ev.update_state(T(yt[25:]), T(yp[25:]))
+    g["stale1_true_rows"], g["stale1_pred_rows"] = np.asarray(ev.all_true_bboxes_variable), np.asarray(ev.all_pred_bboxes_variable)
+    g["stale1_map"] = np.float32(np.asarray(ev.result()))                                  # tmp.py:187-405
+    g["stale1_count"] = np.float32(np.asarray(ev.count))
+
+    # ---- Q5: signed zeros and non-finite values through decode (utils.py:184-197 multiplies the boxes that were NOT
+    # selected by 0 and sums) and NMS.  What the source does with them, on the stand-in's IEEE arithmetic:
+    #   sel: the SELECTED box / the class scores / the confidences carry -0.0, inf or NaN -> pinned below (the CUDA
+    #        path reproduces these: it computes on the same values);
+    #   los: a NON-selected box carries inf / NaN -> the source's 0 * inf = NaN poisons the row; the CUDA path selects
+    #        instead of multiplying and returns the selected box.  Recorded so that the deviation is pinned, and
+    #        documented as "finite inputs only" in include/yolohot.h / INTEGRATION.md.
+    q = F.synth_dense(6, seed=77).astype(F32)
+    sel = q.copy()
+    sel[0, 0, 0, 20:25] = [0.9, -0.0, -0.0, 0.3, 0.3]; sel[0, 0, 0, 25] = 0.1        # selected box: -0.0 coordinates
+    sel[1, 1, 1, 20:25] = [0.9, 0.5, 0.5, np.inf, 0.3]; sel[1, 1, 1, 25] = 0.1       # selected box: infinite width
+    sel[2, 2, 2, 20] = np.inf; sel[2, 2, 2, 25] = 0.5                                # infinite confidence wins
+    sel[3, 3, 3, 0:20] = -0.0                                                        # all class scores -0.0 -> class 0
+    sel[4, 4, 4, 5] = np.inf                                                         # infinite class score -> class 5
+    sel[5, :, :, 20] = -0.0; sel[5, :, :, 25] = 0.0                                  # +-0 confidences tie -> box 0, never kept
+    g["nonfinite_sel_in"] = sel
+    with np.errstate(all="ignore"):
+        d = np.asarray(RU.decode_predictions(T(sel), 20, 2))
+        g["nonfinite_sel_decode"] = d
+        g["nonfinite_sel_rows"], g["nonfinite_sel_count"] = nms_batch(d)
+        los = q.copy()
+        los[0, 0, 0, 20] = 0.9; los[0, 0, 0, 25] = 0.1; los[0, 0, 0, 26:30] = [np.inf, np.nan, -np.inf, 1.0]   # losing box
+        g["nonfinite_los_in"] = los
+        g["nonfinite_los_decode"] = np.asarray(RU.decode_predictions(T(los), 20, 2))
 
     # ---- N2: label grids (dataset.py:88-123) ------------------------------------------------
     gen = label_generator(7, 3, 2)

@@ -399,6 +399,13 @@ class TensorArray:
             return _torch.stack([v if _is_torch(v) else _torch.from_numpy(v) for v in items])
         return _t(np.stack(items))
 
+    def gather(self, indices):
+        idx = np.asarray(_val(indices)).reshape(-1)
+        if idx.size == 0:
+            es = self._eshape if self._eshape is not None else _ELEMENT_SHAPES.get(self._site, ())
+            return _t(np.zeros((0,) + tuple(es), dtype=self._dt))
+        return _t(np.stack([np.asarray(self.read(int(i))) for i in idx]))
+
     def close(self):
         return None
 

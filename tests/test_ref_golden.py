@@ -115,7 +115,7 @@ def test_committed_golden_is_what_the_reference_source_returns(tmp_path):
     new = np.load(out)
     assert sorted(new.files) == sorted(R.files)
     for k in R.files:
-        assert np.array_equal(new[k], R[k]), k
+        assert np.array_equal(new[k], R[k], equal_nan=True), k
 
 
 # ------------------------------------------------------------------ GPU: CUDA path vs reference
@@ -282,3 +282,45 @@ def test_cuda_head_adapter(dev):
     assert abs(float(tot.detach()) - float(R["loss16_total"])) <= 1e-5 * abs(float(R["loss16_total"]))
     np.testing.assert_allclose(yp.grad.cpu().numpy().reshape(R["loss16_grad_torch"].shape), R["loss16_grad_torch"],
                                rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_cuda_stale_metric_evaluators_match_executed_source(dev):
+    """Row a7 on the device: yolohot.metric / get_all_bboxes against metric.py + tmp.py executed on the stand-in."""
+    from yolohot import metric as ym, utils as yu
+    assert np.array_equal(yu.get_all_bboxes(_cuda(R["map40_yp"][:8], dev)).cpu().numpy(), R["stale_gab"])
+    for cls, key in ((ym.MeanAveragePrecision2, "stale2"), (ym.MeanAveragePrecision, "stale1")):
+        ev = cls()
+        ev.update_state(_cuda(R["map40_yt"][:25], dev), _cuda(R["map40_yp"][:25], dev))
+        ev.update_state(_cuda(R["map40_yt"][25:], dev), _cuda(R["map40_yp"][25:], dev))
+        assert np.array_equal(ev.all_true_bboxes_variable.cpu().numpy(), R[f"{key}_true_rows"]), key
+        assert np.array_equal(ev.all_pred_bboxes_variable.cpu().numpy(), R[f"{key}_pred_rows"]), key
+        assert abs(float(ev.result()) - float(R[f"{key}_map"])) <= 1e-6, key
+        got = yu.mean_average_precision_2(ev.all_true_bboxes_variable, ev.all_pred_bboxes_variable)     # tmp.py:440 signature
+        assert abs(float(got) - float(R[f"{key}_map"])) <= 1e-6
+    assert ev.count == 2
+
+
+@pytest.mark.gpu
+def test_cuda_signed_zero_and_non_finite_inputs(dev):
+    """Quirk Q5.  -0.0 / inf in the SELECTED box, the class scores or the confidences: same rows as the reference's
+    source.  A non-finite value in a box that was NOT selected: the source's 0 * inf poisons the row with NaN, the
+    kernels select and return the selected box - the documented finite-input contract (include/yolohot.h); pinned here
+    so that it cannot change silently."""
+    from yolohot import utils as yu
+    x = _cuda(R["nonfinite_sel_in"], dev)
+    assert np.array_equal(yu.decode_predictions(x, 20, 2).cpu().numpy(), R["nonfinite_sel_decode"], equal_nan=True)
+    rows, cnt = yu.decode_nms(x, 20, 2)
+    assert np.array_equal(cnt.cpu().numpy(), R["nonfinite_sel_count"])
+    assert np.array_equal(_kept(rows.cpu().numpy(), cnt.cpu().numpy()), _kept(R["nonfinite_sel_rows"], R["nonfinite_sel_count"]),
+                          equal_nan=True)
+    for i in range(6):                                                    # the per-image surface takes the same rows
+        k = yu.non_max_suppression(_cuda(R["nonfinite_sel_decode"][i], dev)).cpu().numpy()
+        assert np.array_equal(k, R["nonfinite_sel_rows"][i, :R["nonfinite_sel_count"][i]], equal_nan=True)
+    los = yu.decode_predictions(_cuda(R["nonfinite_los_in"], dev), 20, 2).cpu().numpy()
+    ref = R["nonfinite_los_decode"]
+    bad = np.isnan(ref)
+    assert bad.sum() == 3 and np.array_equal(los[~bad], ref[~bad])        # every other value agrees
+    clean = R["nonfinite_los_in"].copy()
+    clean[0, 0, 0, 26:30] = 0.0                                           # the same grid without the losing box's junk
+    assert np.isfinite(los[0, 0]).all() and np.array_equal(los, yu.decode_predictions(_cuda(clean, dev), 20, 2).cpu().numpy())
