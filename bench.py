@@ -167,34 +167,100 @@ def run_reference(args):
     return 0
 
 
-def bind_to_gpu_numa_node(local):
-    """Pin this rank (and therefore the first-touch placement of its pinned host buffers) to the CPUs of the
-    NUMA node its GPU hangs off, so that the e2e H2D/D2H copies of 8 ranks do not cross the socket
-    interconnect.  Placement only; returns a description for the JSON line (None if nothing was done)."""
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _gpu_numa_node(local):
+    """(node, how) of GPU `local`, trying sysfs, NVML's memory affinity and `nvidia-smi topo -m` in turn."""
+    tried = []
     try:
         import pynvml
         pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bus = bus.lower()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
         if len(bus.split(":")[0]) == 8:                       # nvml pads the PCI domain to 8 hex digits
             bus = bus[4:]
-        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return None
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            cpus = set()
-            for part in f.read().strip().split(","):
-                lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
-        allowed = os.sched_getaffinity(0) & cpus
-        if not allowed:
-            return None
-        os.sched_setaffinity(0, allowed)
-        return {"numa_node": node, "cpus": len(allowed)}
+        try:
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+            if node >= 0:
+                return node, "sysfs numa_node"
+            tried.append("sysfs numa_node = -1")
+        except Exception as e:
+            tried.append(f"sysfs: {type(e).__name__}")
+        try:
+            mask = pynvml.nvmlDeviceGetMemoryAffinity(h, 4, pynvml.NVML_AFFINITY_SCOPE_NODE)
+            for w, word in enumerate(mask):
+                for b in range(64):
+                    if (int(word) >> b) & 1:
+                        return 64 * w + b, "nvmlDeviceGetMemoryAffinity"
+            tried.append("nvml memory affinity empty")
+        except Exception as e:
+            tried.append(f"nvml affinity: {type(e).__name__}")
+    except Exception as e:
+        tried.append(f"nvml: {type(e).__name__}")
+    try:
+        import subprocess
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        hdr = None
+        for line in out.splitlines():
+            cols = [c for c in line.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t") if c != ""]
+            if hdr is None and any("NUMA Affinity" in c for c in cols):
+                hdr = [c.strip() for c in cols]
+                continue
+            if hdr is not None and cols and cols[0].strip() == f"GPU{local}":
+                k = [i for i, c in enumerate(hdr) if "NUMA Affinity" in c][0] + 1     # the header row has no row label
+                v = cols[k].strip() if k < len(cols) else ""
+                if v and v.split(",")[0].split("-")[0].isdigit():
+                    return int(v.split(",")[0].split("-")[0]), "nvidia-smi topo -m"
+                tried.append(f"topo NUMA Affinity = {v!r}")
+        if hdr is None:
+            tried.append("topo: no NUMA Affinity column")
+    except Exception as e:
+        tried.append(f"topo: {type(e).__name__}")
+    return None, "; ".join(tried)
+
+
+def bind_to_gpu_numa_node(local):
+    """Place this rank - its threads and, through the memory policy, the pages of the pinned host buffers it allocates
+    afterwards - on the NUMA node its GPU hangs off, so that the e2e H2D / D2H copies of 8 ranks do not cross the socket
+    interconnect.  Placement only.  Always returns a description of what was (or could not be) done for the JSON line."""
+    info = {"nodes_online": None, "gpu_node": None, "how": None, "cpus_bound": None, "mempolicy": None}
+    try:
+        with open("/sys/devices/system/node/online") as f:
+            info["nodes_online"] = f.read().strip()
     except Exception:
-        return None
+        info["nodes_online"] = "unreadable"
+    node, how = _gpu_numa_node(local)
+    info["gpu_node"], info["how"] = node, how
+    if node is None:
+        return info
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            allowed = os.sched_getaffinity(0) & _cpulist(f.read())
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus_bound"] = len(allowed)
+        else:
+            info["cpus_bound"] = "none of the node's CPUs are in this process's cpuset"
+    except Exception as e:
+        info["cpus_bound"] = f"{type(e).__name__}"
+    try:                                                          # set_mempolicy(MPOL_PREFERRED, {node}): also works when the
+        libc = ctypes.CDLL(None, use_errno=True)                  # cpuset is a single socket
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        rc = libc.syscall(238, 1, mask, 16 * 64 + 1)              # __NR_set_mempolicy (x86-64), MPOL_PREFERRED
+        info["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy errno %d" % ctypes.get_errno()
+    except Exception as e:
+        info["mempolicy"] = f"{type(e).__name__}"
+    return info
 
 
 # ------------------------------------------------------------------------------------ own arm
@@ -209,7 +275,7 @@ def run_own(args):
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    numa = bind_to_gpu_numa_node(local) if (world > 1 and env_int("YH_BENCH_NUMA_BIND", 1)) else None
+    numa = bind_to_gpu_numa_node(local) if env_int("YH_BENCH_NUMA_BIND", 1) else {"how": "disabled (YH_BENCH_NUMA_BIND=0)"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -299,16 +365,35 @@ def run_own(args):
                                         h_cnt.data_ptr(), None, local), "yh_decode_nms_host")
 
     e2e_step()
-    # the e2e path's own roofline: a bare pinned H2D copy of the same input (PCIe), device-timed
+    # the e2e path's own roofline: a bare pinned H2D copy of the same input (PCIe), device-timed - once with every rank
+    # copying at the same time (what the host memory system / PCIe fabric delivers to N GPUs at once: the ceiling of the
+    # N-GPU e2e figure) and once rank by rank (what one GPU gets when it has the host to itself)
     d_tmp = torch.empty_like(pred[:e2e_n])
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    d_tmp.copy_(h_in, non_blocking=True)
-    torch.cuda.synchronize(dev)
-    c0.record(stream)
-    d_tmp.copy_(h_in, non_blocking=True)
-    c1.record(stream)
-    torch.cuda.synchronize(dev)
-    h2d_gbs = e2e_n * IMG_IN / (c0.elapsed_time(c1) * 1e-3) / 1e9
+
+    def bare_h2d():
+        c0.record(stream)
+        d_tmp.copy_(h_in, non_blocking=True)
+        c1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e2e_n * IMG_IN / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    bare_h2d()
+    barrier()
+    h2d_gbs = bare_h2d()                                             # all ranks at once
+    h2d_all = h2d_gbs
+    h2d_solo = h2d_gbs
+    if world > 1:
+        t = torch.tensor([h2d_gbs], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        h2d_all = float(t[0])                                        # aggregate over the ranks
+        solo = torch.zeros(world, device=dev, dtype=torch.float64)
+        for r in range(world):                                       # one rank at a time
+            dist.barrier()
+            if r == rank:
+                solo[r] = bare_h2d()
+        dist.all_reduce(solo)
+        h2d_solo = float(solo[rank])
+        solo_all = [float(v) for v in solo]
     del d_tmp
     e2e_steps = max(2, min(args.steps, env_int("YH_BENCH_E2E_STEPS", 5)))
     with ClockSampler(local) as clk2:
@@ -319,19 +404,30 @@ def run_own(args):
         torch.cuda.synchronize(dev)
         e2e_s = (time.perf_counter() - t0) / e2e_steps
     ok_e2e = bool(torch.equal(h_cnt, cnt[:e2e_n].cpu()))
+    zero_tail = bool((h_boxes[0, int(h_cnt[0]):] == 0).all())        # rows past count[i] come back as zeros
+    numa_all = [numa]
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)
     e2e = {"value": world * e2e_n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e_n * IMG_IN,
            "d2h_bytes_per_step": e2e_n * (M * 24 + 4), "images_per_step_per_gpu": e2e_n, "steps": e2e_steps,
            "ms_per_step": 1000.0 * e2e_s, "api": "yh_decode_nms_host (C-ABI, pinned host buffers in/out)",
-           "counts_match_device_path": ok_e2e, "numa_binding_rank0": numa, "bare_pinned_h2d_copy_GBps": h2d_gbs,
-           "frac_of_bare_h2d_copy": (e2e_n * IMG_IN / e2e_s / 1e9) / h2d_gbs}
-    # the same call with a float16 head (half the bytes over PCIe; widened exactly inside the kernel) - context only,
-    # the headline e2e above stays on the reference's float32 tensors
+           "counts_match_device_path": ok_e2e, "rows_past_count_are_zero": zero_tail,
+           "numa_binding_rank0": numa, "numa_gpu_node_per_rank": [(x or {}).get("gpu_node") for x in numa_all],
+           "bare_pinned_h2d_copy_GBps": h2d_gbs, "bare_pinned_h2d_all_ranks_at_once_GBps_total": h2d_all,
+           "bare_pinned_h2d_one_rank_at_a_time_GBps": h2d_solo,
+           "frac_of_bare_h2d_copy": (e2e_n * IMG_IN / e2e_s / 1e9) / h2d_gbs,
+           "frac_of_concurrent_h2d_ceiling": (world * e2e_n * IMG_IN / e2e_s / 1e9) / h2d_all,
+           "limit": "PCIe / host memory: e2e runs at the rate a bare pinned H2D copy of the same bytes gets when all ranks copy at once"}
+    if world > 1:
+        e2e["bare_pinned_h2d_one_rank_at_a_time_GBps_per_rank"] = solo_all
+    # the same call with a float16 head (half the bytes over PCIe; widened exactly inside the kernel), at every N; the
+    # headline e2e above stays on the reference's float32 tensors
     e2e_half = None
-    if world == 1 and env_int("YH_BENCH_E2E_HALF", 1):
+    if env_int("YH_BENCH_E2E_HALF", 1):
         h_half = torch.empty((e2e_n, S, S, D), dtype=torch.float16, pin_memory=True)
         h_half.copy_(h_in)
 
@@ -339,13 +435,18 @@ def run_own(args):
             _lib.check(L.yh_decode_nms_host_typed(h_half.data_ptr(), _lib.YH_DTYPE_F16, e2e_n, S, B, C, IOU_THR, CONF_THR,
                                                   h_boxes.data_ptr(), h_cnt.data_ptr(), None, local), "yh_decode_nms_host_typed")
         half_step()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             half_step()
         torch.cuda.synchronize(dev)
         hs = (time.perf_counter() - t0) / e2e_steps
-        e2e_half = {"value": e2e_n / hs, "unit": UNIT, "ms_per_step": 1000.0 * hs, "h2d_bytes_per_step": e2e_n * IMG_IN // 2,
-                    "api": "yh_decode_nms_host_typed (float16 head, pinned host buffers)",
+        if world > 1:
+            t = torch.tensor([hs], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            hs = float(t[0])
+        e2e_half = {"value": world * e2e_n / hs, "unit": UNIT, "ms_per_step": 1000.0 * hs, "h2d_bytes_per_step": e2e_n * IMG_IN // 2,
+                    "n_gpus": world, "api": "yh_decode_nms_host_typed (float16 head, pinned host buffers)",
                     "note": "float16 rounding of the synthetic inputs changes the results; parity is against the widened tensor"}
         del h_half
     del h_in, h_boxes

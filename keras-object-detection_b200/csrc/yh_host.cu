@@ -5,6 +5,12 @@
 // The batch is cut into chunks; chunk c uses slot c % kSlots = {stream, device in/out
 // buffers}.  H2D copy, kernel and D2H copies of one chunk are ordered on its stream; the
 // slots' streams overlap, so the copy engines (one per direction) and the SMs all stay busy.
+// That overlap needs PINNED host buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory):
+// with pageable memory the call is still correct, but the driver stages every copy through its
+// own pinned bounce buffer and the copies run one after the other.
+// State is per device (slots, streams, one lock per device): calls for different devices run
+// concurrently, calls for one device are serialised.  Rows past count[i] of an image come back
+// as zeros (the device slot is cleared before each kernel), like the np.zeros the caller made.
 #include <algorithm>
 #include <mutex>
 
@@ -28,7 +34,7 @@ struct HostCtx {
 };
 
 static HostCtx g_ctx[64];
-static std::mutex g_mu;
+static std::mutex g_mu[64];               // one per device: a single-process multi-GPU host does not serialise its devices
 
 static int grow(void **p, size_t &cap, size_t need, bool &changed)
 {
@@ -54,7 +60,7 @@ static int host_impl(const void *pred_host_v, int dtype, int64_t n, int S, int B
     YH_REQUIRE(device >= 0 && device < 64, "decode_nms_host: bad device %d", device);
     if (n == 0) return YH_OK;
     YH_REQUIRE(pred_host && out_boxes_host && out_count_host, "decode_nms_host: null pointer");
-    std::lock_guard<std::mutex> lock(g_mu);
+    std::lock_guard<std::mutex> lock(g_mu[device]);
     int prev = 0;
     YH_CUDA(cudaGetDevice(&prev));
     YH_CUDA(cudaSetDevice(device));
@@ -87,11 +93,16 @@ static int host_impl(const void *pred_host_v, int dtype, int64_t n, int S, int B
 
     int rc = YH_OK;
     int64_t c = 0;
+    // any failure leaves the loop through `rc`: the slots' streams are ALWAYS synchronised below, so no copy into
+    // the caller's buffers and no kernel on the cached slots is still in flight when the call returns
+    auto ck = [&](cudaError_t e, const char *what) { if (e != cudaSuccess && rc == YH_OK) rc = cuda_fail(e, what); return e == cudaSuccess; };
     for (int64_t lo = 0; lo < n && rc == YH_OK; lo += chunk, ++c) {
         const int s = static_cast<int>(c % kSlots);
         const int64_t cnt = std::min(chunk, n - lo);
         cudaStream_t st = cx.st[s];
-        YH_CUDA(cudaMemcpyAsync(cx.d_in[s], pred_host + lo * img_in, cnt * img_in, cudaMemcpyHostToDevice, st));
+        if (!ck(cudaMemcpyAsync(cx.d_in[s], pred_host + lo * img_in, cnt * img_in, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync H2D")) break;
+        if (!ck(cudaMemsetAsync(cx.d_boxes[s], 0, cnt * img_boxes, st), "cudaMemsetAsync")) break;      // rows past count[i] read as zeros
+        if (out_keep_idx_host && !ck(cudaMemsetAsync(cx.d_idx[s], 0xff, cnt * M * 4, st), "cudaMemsetAsync")) break;   // and indices as -1
         if (dtype == YH_DTYPE_F32)
             rc = decode_nms_device(cx.d_in[s], cnt, S, B, C, iou_thr, conf_thr, cx.d_boxes[s], cx.d_count[s],
                                    out_keep_idx_host ? cx.d_idx[s] : nullptr, st, YH_SCORE_CONF);
@@ -99,10 +110,10 @@ static int host_impl(const void *pred_host_v, int dtype, int64_t n, int S, int B
             rc = yh_decode_nms_typed(cx.d_in[s], dtype, cnt, S, B, C, iou_thr, conf_thr, YH_SCORE_CONF, cx.d_boxes[s],
                                      cx.d_count[s], out_keep_idx_host ? cx.d_idx[s] : nullptr, st);
         if (rc != YH_OK) break;
-        YH_CUDA(cudaMemcpyAsync(out_boxes_host + lo * M * 6, cx.d_boxes[s], cnt * img_boxes, cudaMemcpyDeviceToHost, st));
-        YH_CUDA(cudaMemcpyAsync(out_count_host + lo, cx.d_count[s], cnt * 4, cudaMemcpyDeviceToHost, st));
-        if (out_keep_idx_host)
-            YH_CUDA(cudaMemcpyAsync(out_keep_idx_host + lo * M, cx.d_idx[s], cnt * M * 4, cudaMemcpyDeviceToHost, st));
+        if (!ck(cudaMemcpyAsync(out_boxes_host + lo * M * 6, cx.d_boxes[s], cnt * img_boxes, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync D2H")) break;
+        if (!ck(cudaMemcpyAsync(out_count_host + lo, cx.d_count[s], cnt * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync D2H")) break;
+        if (out_keep_idx_host &&
+            !ck(cudaMemcpyAsync(out_keep_idx_host + lo * M, cx.d_idx[s], cnt * M * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync D2H")) break;
     }
     for (int s = 0; s < kSlots; ++s) {
         cudaError_t e = cudaStreamSynchronize(cx.st[s]);
