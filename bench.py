@@ -354,10 +354,23 @@ def run_own(args):
             e2e_n //= 2
     except Exception:
         pass
-    h_in = torch.empty((e2e_n, S, S, D), dtype=torch.float32, pin_memory=True)
+    wc_ptr = None
+    if env_int("YH_BENCH_E2E_WC", 0):       # experiment: write-combined pinned input buffer (yh_host_alloc)
+        import numpy as _np
+        wc_ptr = ctypes.c_void_p()
+        _lib.check(L.yh_host_alloc(e2e_n * IMG_IN, 1, ctypes.byref(wc_ptr)), "yh_host_alloc")
+        buf = (ctypes.c_float * (e2e_n * M * D)).from_address(wc_ptr.value)
+        h_in = torch.from_numpy(_np.frombuffer(buf, dtype=_np.float32).reshape(e2e_n, S, S, D))
+    else:
+        h_in = torch.empty((e2e_n, S, S, D), dtype=torch.float32, pin_memory=True)
     h_boxes = torch.empty((e2e_n, M, 6), dtype=torch.float32, pin_memory=True)
     h_cnt = torch.empty((e2e_n,), dtype=torch.int32, pin_memory=True)
-    h_in.copy_(pred[:e2e_n])
+    if wc_ptr is None:
+        h_in.copy_(pred[:e2e_n])
+    else:                                    # the CPU only ever writes this buffer
+        for lo in range(0, e2e_n, 65_536):
+            hi = min(e2e_n, lo + 65_536)
+            h_in[lo:hi] = pred[lo:hi].cpu()
     torch.cuda.synchronize(dev)
 
     def e2e_step():

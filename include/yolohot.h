@@ -103,6 +103,13 @@ YH_API int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int B, i
                        float *out_boxes_host, int32_t *out_count_host,
                        int32_t *out_keep_idx_host /* nullable */, int device);
 
+/* The chunk pipeline of the *_host entry points overlaps its copies only with PINNED host memory
+ * (pageable buffers work, but the driver stages them and the copies run one after the other).
+ * yh_host_alloc = cudaHostAlloc (portable; write_combined = 1 for input staging buffers that the
+ * CPU only writes: faster over PCIe on some hosts, very slow to read back on the CPU). */
+YH_API int yh_host_alloc(size_t bytes, int write_combined, void **ptr);
+YH_API int yh_host_free(void *ptr);
+
 /* ---- confidence filter without NMS: metric.py:35-37, 81 (the stale evaluator's ground truth) ----
  * rows (n, M, 6) -> out_rows (n, M, 6): the rows of image i with conf > conf_thr, cell order kept,
  * packed at the front; out_count (n).  out_rows must not alias rows. */

@@ -134,3 +134,20 @@ extern "C" int yh_decode_nms_host_typed(const void *pred_host, int dtype, int64_
 {
     return host_impl(pred_host, dtype, n, S, B, C, iou_thr, conf_thr, out_boxes_host, out_count_host, out_keep_idx_host, device);
 }
+
+// Pinned host buffers for the callers of the *_host entry points (what the chunk pipeline above needs to overlap its
+// copies).  write_combined = 1 asks for cudaHostAllocWriteCombined: not snooped on its way over PCIe (faster H2D on
+// some hosts) but very slow to READ from the CPU - for input staging buffers that the CPU only writes.
+extern "C" int yh_host_alloc(size_t bytes, int write_combined, void **ptr)
+{
+    YH_REQUIRE(ptr != nullptr && bytes > 0, "host_alloc: bad arguments");
+    *ptr = nullptr;
+    YH_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+    return YH_OK;
+}
+
+extern "C" int yh_host_free(void *ptr)
+{
+    if (ptr) YH_CUDA(cudaFreeHost(ptr));
+    return YH_OK;
+}

@@ -21,6 +21,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "yh_common.cuh"
@@ -154,14 +155,28 @@ __global__ void __launch_bounds__(RS_T, 2) map_radix_kernel(ReduceArgs a)
         if (tid < RS_BINS) a.hist[static_cast<size_t>(cta) * RS_BINS + tid] = sm.hist[tid];
         grid.sync();
         // ---- output cursors of this CTA: digits ascending, within a digit CTAs ascending (stable)
+        // (all 512 threads: digit = tid & 255, rows of parity tid >> 8, eight loads in flight; one L2 round trip per
+        // eight rows instead of one per row - at a few thousand records per CTA this loop IS the pass)
         uint32_t tot = 0, mine = 0;
-        if (tid < RS_BINS) {
-#pragma unroll 4
-            for (int c = 0; c < G; ++c) {
-                const uint32_t v = a.hist[static_cast<size_t>(c) * RS_BINS + tid];
-                if (c < cta) mine += v;
-                tot += v;
+        {
+            const int dgt = tid & (RS_BINS - 1), par = tid >> 8;
+            for (int c0 = par; c0 < G; c0 += 16) {
+                uint32_t v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + 2 * j;
+                    v[j] = (c < G) ? __ldcg(a.hist + static_cast<size_t>(c) * RS_BINS + dgt) : 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (c0 + 2 * j < cta) mine += v[j];
+                    tot += v[j];
+                }
             }
+            if (par == 1) { sm.tile_cnt[dgt] = tot; sm.tile_start[dgt] = mine; }      // scratch until the tile loop
+            __syncthreads();
+            if (par == 0) { tot += sm.tile_cnt[dgt]; mine += sm.tile_start[dgt]; }
+            __syncthreads();
         }
         uint32_t all;
         const uint32_t base = scan256(tid < RS_BINS ? tot : 0u, sm, all);
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(RS_T, 2) map_radix_kernel(ReduceArgs a)
             uint32_t d[RS_IPT], r[RS_IPT];
             const long long wbase = t0 + static_cast<long long>(warp) * (32 * RS_IPT);
 #pragma unroll
-            for (int j = 0; j < RS_IPT; ++j) {
+            for (int j = 0; j < RS_IPT; ++j) {                   // all loads of the thread in flight together
                 const long long pos = wbase + j * 32 + lane;
                 const bool valid = pos < hi;
                 k[j] = valid ? load_in(a, sm, src, pos) : ~0ull;
@@ -184,13 +199,15 @@ __global__ void __launch_bounds__(RS_T, 2) map_radix_kernel(ReduceArgs a)
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < RS_IPT; ++j) {
-                const uint32_t peers = __match_any_sync(0xffffffffu, d[j]);
-                const bool valid = d[j] < 256u;
-                const uint32_t before = valid ? sm.wc[warp][d[j]] : 0u;
-                r[j] = before + __popc(peers & lt_mask);
-                __syncwarp();
-                if (valid && lane == __ffs(peers) - 1) sm.wc[warp][d[j]] = before + __popc(peers);
-                __syncwarp();
+                if (wbase + j * 32 < hi) {                       // warp-uniform: a short last tile costs what it holds
+                    const uint32_t peers = __match_any_sync(0xffffffffu, d[j]);
+                    const bool valid = d[j] < 256u;
+                    const uint32_t before = valid ? sm.wc[warp][d[j]] : 0u;
+                    r[j] = before + __popc(peers & lt_mask);
+                    __syncwarp();
+                    if (valid && lane == __ffs(peers) - 1) sm.wc[warp][d[j]] = before + __popc(peers);
+                    __syncwarp();
+                }
             }
             __syncthreads();
             uint32_t cnt = 0;
@@ -396,6 +413,10 @@ static int radix_grid(int64_t n_want, size_t smem, int &G)
     const int cap = std::min(occ, 2) * sm_count();
     const int64_t want = (n_want + RS_TILE - 1) / RS_TILE;
     G = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(cap, want)));
+    if (const char *v = getenv("YH_MAP_GRID")) {                 // experiments: any grid is correct
+        const int g = atoi(v);
+        if (g >= 1) G = std::min(cap, g);
+    }
     return YH_OK;
 }
 
