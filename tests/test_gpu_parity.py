@@ -418,7 +418,7 @@ def test_sharded_map_single_process_emulation(dev):
 
 # ------------------------------------------------------------ BASELINE.json configs at full size
 def _dense_cfg5(n, dev, seed=99):
-    """cfg5 data on the device (same recipe as profiles/bench_configs.py)."""
+    """cfg5 data on the device (same recipe as bench.py cfg5_stress)."""
     S, B, C = 14, 3, 80
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
