@@ -774,6 +774,7 @@ __global__ void __launch_bounds__(864, 1) decode_nms_tma_kernel(const E *__restr
 //   F  output slots from the final keep words; every cell thread writes its own row
 // ------------------------------------------------------------------------------------------
 constexpr int kTeamWarpsMax = 8;
+constexpr int kRankBuckets = 64;          // phase B of the team kernel: confidence buckets of the rank
 
 struct CoopCfg {
     int ST, NTEAM, TW;      // ring stages, teams per CTA, warps per team (= chunks per image)
@@ -870,6 +871,8 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const E *__res
     int *wcnt = reinterpret_cast<int *>(tp);                 tp += kTeamWarpsMax * 4;
     unsigned *kws = reinterpret_cast<unsigned *>(tp);        tp += kTeamWarpsMax * 4;
     unsigned *help = reinterpret_cast<unsigned *>(tp);       tp += MPT * (kTeamWarpsMax / 2) * 4;   // re-dealt words of phase D
+    int *bhist = reinterpret_cast<int *>(tp);                tp += kRankBuckets * 4;                 // phase B: candidates per bucket
+    int *bbase = reinterpret_cast<int *>(tp);                tp += kRankBuckets * 4;                 //          candidates in higher buckets
     unsigned *tbl = reinterpret_cast<unsigned *>(tp);        // [C][TW]
     for (int i = q; i < cfg.C * cc.TW; i += nthr) tbl[i] = 0u;
     team_sync(bar_id, nthr);
@@ -880,6 +883,7 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const E *__res
 
     for (int64_t i = team; i < my_imgs; i += cc.NTEAM) {
         const int64_t img = blockIdx.x + i * gridDim.x;
+        if (q < kRankBuckets) bhist[q] = 0;                        // read last in phase B of the previous image; the A' barrier orders this
         // ---- A: decode own cell from the ring
         const int64_t c = i * cc.TW + wt;
         const int s = static_cast<int>(c % cc.ST);
@@ -916,38 +920,45 @@ __global__ void __launch_bounds__(1024, 1) decode_nms_coop_kernel(const E *__res
             team_sync(bar_id, nthr);                               // wcnt is rewritten by the next image
             continue;
         }
-        if (pass) ckey[ci] = conf;
-        if (q < 4) ckey[n + q] = -INFINITY;                        // pad to a multiple of 4 for the float4 loop
-        team_sync(bar_id, nthr);
-        // ---- B: stable descending rank (utils.py:98)
-        int r;
-        {
-            int acc = 0;
-            const float4 *k4p = reinterpret_cast<const float4 *>(ckey);
-            const int n4 = (n + 3) >> 2;
-#pragma unroll 4
-            for (int g = 0; g < n4; ++g) {
-                const float4 k = k4p[g];
-                acc = acc + gt_bits(k.x, conf) + gt_bits(k.y, conf);
-                acc = acc + gt_bits(k.z, conf) + gt_bits(k.w, conf);
-            }
-            r = ((static_cast<unsigned>(acc) >> 23) * 383u) & 511u;
+        // ---- B: stable descending rank (utils.py:98): r = #{s_j > s_i} + #{j < i : s_j = s_i}.
+        //      Not by comparing every pair (n^2 / 32 comparisons per warp): the candidates are first dropped into
+        //      kRankBuckets confidence buckets (monotone in the confidence, so every candidate of a higher bucket ranks
+        //      before every candidate of a lower one), a suffix sum over the bucket counts gives the rank of a bucket's
+        //      first member, and only the handful of candidates that share a bucket are compared with each other -
+        //      (confidence, source index) lexicographically, which is the stable order itself: no tie pass.
+        int bkt = 0, slot = 0;
+        if (pass) {
+            bkt = min(max(static_cast<int>(__fmul_rn(conf, static_cast<float>(kRankBuckets))), 0), kRankBuckets - 1);
+            slot = atomicAdd(&bhist[bkt], 1);
         }
-        if (!pass) r = 0;                                          // keeps every index below in range
-        if (pass) smeta[r] = ci;
         team_sync(bar_id, nthr);
-        const bool dup = team_any(bar_id, nthr, pass && smeta[r] != ci);
-        if (dup) {                                                 // equal confidences exist: lower source index first
-            // rounds of shared-memory atomicMin over the positions of each tie group, as in nms_warp
-            if (q < n) smeta[q] = 0x7fffffff;
-            team_sync(bar_id, nthr);
-            bool pend = pass;
-            for (;;) {
-                if (pend) atomicMin(&smeta[r], ci);
-                team_sync(bar_id, nthr);
-                pend = pend && smeta[r] != ci;
-                if (pend) r += 1;
-                if (!team_any(bar_id, nthr, pend)) break;          // its barrier also ends this round's reads
+        if (wt == 0) {                                             // suffix sums over 64 buckets: two per lane
+            const int h0 = bhist[2 * lane], h1 = bhist[2 * lane + 1];
+            int suf = h0 + h1;                                     // inclusive suffix sum over the lanes above
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(FULL, suf, o);
+                if (lane + o < 32) suf += t;
+            }
+            const int above = suf - (h0 + h1);
+            bbase[2 * lane + 1] = above;
+            bbase[2 * lane] = above + h1;
+        }
+        team_sync(bar_id, nthr);
+        if (pass) {
+            const int pos = bbase[bkt] + slot;
+            ckey[pos] = conf;
+            outpos[pos] = ci;
+        }
+        team_sync(bar_id, nthr);
+        int r = 0;
+        if (pass) {
+            const int st0 = bbase[bkt], nb = bhist[bkt];
+            r = st0;
+            for (int m = 0; m < nb; ++m) {
+                const float k = ckey[st0 + m];
+                const int i2 = outpos[st0 + m];
+                r += ((k > conf) || (k == conf && i2 < ci)) ? 1 : 0;
             }
         }
         // ---- C: scatter to rank order (utils.py:24-32,40); class masks
@@ -1156,6 +1167,7 @@ static int launch_coop(const E *pred, int64_t n, NmsCfg cfg, float *out_boxes, i
     if (n_coop < 1 || (cc.shifted && env_int("YH_COOP_SHIFTED", 1) == 0)) return YH_OK;
     const int MPT = cc.TW * 32;
     cc.team_bytes = (MPT * 16 + MPT * 4 + MPT * 4 + (MPT + 4) * 4 + MPT * 4 + 2 * kTeamWarpsMax * 4 + MPT * (kTeamWarpsMax / 2) * 4 +
+                     2 * kRankBuckets * 4 +
                      cfg.C * cc.TW * 4 + 15) & ~15;
     cc.NTEAM = std::max(1, std::min(std::min(15, 31 / cc.TW), env_int("YH_COOP_TEAMS", 4)));
     cc.ST = std::max(2, std::min(32, env_int("YH_COOP_STAGES", 10)));
