@@ -469,18 +469,21 @@ def run_own(args):
     n_sus = env_int("YH_BENCH_SUSTAINED", 1000)
     if n_sus > 0:
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_sus + 1)]
-        barrier()
-        evs[0].record(stream)
-        for k in range(n_sus):
-            step()
-            evs[k + 1].record(stream)
-        barrier()
+        with ClockSampler(local) as clk3:
+            barrier()
+            evs[0].record(stream)
+            for k in range(n_sus):
+                step()
+                evs[k + 1].record(stream)
+            barrier()
         ts = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(n_sus))
         tot = evs[0].elapsed_time(evs[n_sus])
         gbs = algo_bytes / (tot / n_sus * 1e-3) / 1e9
         sustained = {"launches": n_sus, "seconds": tot / 1e3, "ms_mean": tot / n_sus, "ms_p50": ts[n_sus // 2],
                      "ms_p99": ts[min(n_sus - 1, int(0.99 * n_sus))], "ms_min": ts[0], "images_per_s_per_gpu": n_img / (tot / n_sus * 1e-3),
-                     "GBps": gbs, "frac_hbm": gbs / peak}
+                     "GBps": gbs, "frac_hbm": gbs / peak, "ms_first_20_mean": statistics.mean(evs[k].elapsed_time(evs[k + 1]) for k in range(min(20, n_sus))),
+                     "ms_last_100_mean": statistics.mean(evs[k].elapsed_time(evs[k + 1]) for k in range(max(0, n_sus - 100), n_sus)),
+                     "clocks": clk3.summary()}
         if world > 1:
             t = torch.tensor([sustained["ms_mean"]], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
