@@ -103,6 +103,17 @@ YH_API int yh_decode_nms_host(const float *pred_host, int64_t n, int S, int B, i
                        float *out_boxes_host, int32_t *out_count_host,
                        int32_t *out_keep_idx_host /* nullable */, int device);
 
+/* The same with a COMPACT result: only the kept rows come back.  out_rows_host (row_capacity, 7) receives
+ * rows [img, cls, conf, cx, cy, w, h] of all images in image order (img = index in the batch, as float32
+ * like the reference's accumulator, utils.py:476; within an image the NMS pick order), out_count_host (n)
+ * the kept rows per image, *out_total_rows their sum.  D2H bytes: 28 * kept rows + 4 * n instead of
+ * 24 * S*S * n.  If the rows do not fit row_capacity the call copies what fits, sets *out_total_rows to
+ * the number needed and returns YH_ERR_ARG (S*S * n rows always suffice). */
+YH_API int yh_decode_nms_host_rows(const void *pred_host, int dtype, int64_t n, int S, int B, int C,
+                            float iou_thr, float conf_thr,
+                            float *out_rows_host, int64_t row_capacity, int32_t *out_count_host,
+                            int64_t *out_total_rows, int device);
+
 /* The chunk pipeline of the *_host entry points overlaps its copies only with PINNED host memory
  * (pageable buffers work, but the driver stages them and the copies run one after the other).
  * yh_host_alloc = cudaHostAlloc (portable; write_combined = 1 for input staging buffers that the

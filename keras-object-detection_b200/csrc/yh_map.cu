@@ -19,6 +19,7 @@
 //                        image) -> one thread per detection: binary search of its image's ground truths, best IoU,
 //                        atomicMin of (confidence desc, row asc) into the claim of that ground truth -> TP iff the
 //                        detection owns the ground truth it points at: the sequential claim loop without sequencing.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -299,6 +300,10 @@ static int eval_update_impl(EvalArgs a, bool match, void *stream)
         // tiles: enough CTAs to fill the machine four times over, at most kScanMaxTiles, a multiple of 8 images each
         long long tile = (a.n + 4 * sm_count() - 1) / (4 * sm_count());
         tile = std::max<long long>(8, std::min<long long>(1024, (tile + 7) / 8 * 8));
+        if (const char *v = getenv("YH_EVAL_TILE")) {                       // experiments: any tile size is correct
+            const long long t = atoll(v);
+            if (t >= 8 && t <= 1024 && (a.n + t - 1) / t <= kScanMaxTiles) tile = t / 8 * 8;
+        }
         a.tile = static_cast<int>(tile);
         const int ntiles = static_cast<int>((a.n + tile - 1) / tile);
         const size_t smem = sizeof(int) * (2 * static_cast<size_t>(a.tile) + (match ? a.C : 0));

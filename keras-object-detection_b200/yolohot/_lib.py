@@ -22,7 +22,7 @@ _lib = None
 # every symbol include/yolohot.h declares (tests/test_abi.py checks the two stay in sync)
 SYMBOLS = (
     "yh_version", "yh_last_error", "yh_device_info", "yh_launch_count",
-    "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_ex", "yh_decode_nms_host", "yh_decode_nms_host_typed", "yh_host_alloc", "yh_host_free", "yh_filter_rows", "yh_rows_append",
+    "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_ex", "yh_decode_nms_host", "yh_decode_nms_host_typed", "yh_decode_nms_host_rows", "yh_host_alloc", "yh_host_free", "yh_filter_rows", "yh_rows_append",
     "yh_loss", "yh_eval_update", "yh_map_match", "yh_map_reduce",
     "yh_encode_labels", "yh_head_to_f32", "yh_decode_nms_typed", "yh_pixel_boxes",
     "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_comm_p2p", "yh_comm_barrier",
@@ -59,6 +59,7 @@ def lib():
     L.yh_decode_nms_ex.argtypes = [vp, i64, i, i, i, f, f, i, vp, vp, vp, vp]
     L.yh_decode_nms_host.argtypes = [vp, i64, i, i, i, f, f, vp, vp, vp, i]
     L.yh_decode_nms_host_typed.argtypes = [vp, i, i64, i, i, i, f, f, vp, vp, vp, i]
+    L.yh_decode_nms_host_rows.argtypes = [vp, i, i64, i, i, i, f, f, vp, i64, vp, vp, i]
     L.yh_host_alloc.argtypes = [C.c_size_t, i, vp]
     L.yh_host_free.argtypes = [vp]
     L.yh_filter_rows.argtypes = [vp, i64, i, f, vp, vp, vp]

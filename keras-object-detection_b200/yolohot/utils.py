@@ -123,13 +123,15 @@ def non_max_suppression_2(boxes, iou_threshold=0.5, conf_threshold=0.4):
 
 
 def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_threshold=0.4,
-               return_index=False, out=None, grid=None, score_mode="conf"):
+               return_index=False, out=None, grid=None, score_mode="conf", compact=False):
     """Fused, batched loop body of utils.py:470-480 (decode + per-image NMS).
 
     Returns (boxes (N,S*S,6), count (N,) int32[, keep_idx (N,S*S) int32]): the first count[i]
     rows of image i are its kept rows in pick order; rows past that are unspecified unless
     `out` buffers were zeroed by the caller.  Host array-likes go through the pipelined
-    host entry point (yh_decode_nms_host) and come back as NumPy.
+    host entry point (yh_decode_nms_host) and come back as NumPy (rows past count[i] zero).
+    compact=True (host inputs only): only the kept rows come back over PCIe - returns
+    (rows (K_total, 7) [img, cls, conf, cx, cy, w, h] in image order, count (N,)) (yh_decode_nms_host_rows).
 
     score_mode="conf" is the reference (a cell's score is its best box confidence).
     score_mode="conf_x_prob" is an extension the reference does not have: confidence x winning
@@ -159,6 +161,23 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
         if p.ndim != 4 or p.shape[1] != p.shape[2] or p.shape[3] != num_classes + 5 * num_boxes:
             raise ValueError(f"expected (N, S, S, {num_classes + 5 * num_boxes}) predictions, got {tuple(p.shape)}")
         n, S = p.shape[0], p.shape[1]
+        if compact:
+            if return_index:
+                raise ValueError("decode_nms: compact=True returns rows, not indices")
+            src = p.data_ptr() if host_half else p.ctypes.data
+            cnt = np.zeros((n,), np.int32)
+            cap = max(1024, 8 * n)                           # a guess; the call says how many rows it needs
+            while True:
+                rows = np.empty((cap, 7), np.float32)
+                total = C.c_int64(0)
+                rc = L.yh_decode_nms_host_rows(src, code, n, S, int(num_boxes), int(num_classes), float(iou_threshold),
+                                               float(conf_threshold), rows.ctypes.data, cap, cnt.ctypes.data, C.byref(total),
+                                               torch.cuda.current_device())
+                if rc == _lib.YH_ERR_ARG and total.value > cap:
+                    cap = int(total.value)
+                    continue
+                _lib.check(rc, "decode_nms")
+                return rows[:total.value], cnt
         boxes = np.zeros((n, S * S, 6), np.float32)
         cnt = np.zeros((n,), np.int32)
         kidx = np.full((n, S * S), -1, np.int32) if return_index else None
@@ -168,6 +187,8 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
                                               kidx.ctypes.data if return_index else None, torch.cuda.current_device()),
                    "decode_nms")
         return (boxes, cnt, kidx) if return_index else (boxes, cnt)
+    if compact:
+        raise ValueError("decode_nms: compact=True is for host inputs; on the device use MeanAveragePrecision / yh_rows_append")
     half = isinstance(predictions, torch.Tensor) and predictions.is_cuda and predictions.dtype in (torch.float16, torch.bfloat16)
     if half:                        # half-precision head: widened inside the kernel (yh_decode_nms_typed), half the HBM bytes
         p, kind = predictions.contiguous(), "torch"

@@ -60,6 +60,8 @@ def test_argument_errors_need_no_gpu():
     assert L.yh_ipc_close(None) == _lib.YH_OK and L.yh_ipc_free(None) == _lib.YH_OK
     assert L.yh_decode_nms_host_typed(None, 9, 4, 7, 2, 20, 0.5, 0.4, None, None, None, 0) == _lib.YH_ERR_ARG
     assert b"unknown dtype" in L.yh_last_error()
+    assert L.yh_decode_nms_host_rows(None, 0, 4, 7, 2, 20, 0.5, 0.4, None, 0, None, None, 0) == _lib.YH_ERR_ARG
+    assert L.yh_host_alloc(0, 0, None) == _lib.YH_ERR_ARG and L.yh_host_free(None) == _lib.YH_OK
     assert L.yh_encode_labels(None, None, -1, 7, 2, 20, None, None, None) == _lib.YH_ERR_ARG
     assert L.yh_head_to_f32(None, 7, 16, None, None) == _lib.YH_ERR_ARG
     assert L.yh_pixel_boxes(None, None, 4, 0, 448, 448, None, None) == _lib.YH_ERR_ARG

@@ -214,6 +214,23 @@ def test_decode_nms_host_entry(dev):
         _check_nms(goth, wantw, "host-half")
 
 
+def test_decode_nms_host_compact_rows(dev):
+    """yh_decode_nms_host_rows: only the kept rows cross PCIe; equal to the padded host result, over several chunks,
+    for float32 and float16 inputs, with a row buffer that is too small at first."""
+    from yolohot import utils as yu
+    for gen, n in ((F.synth_sparse, 40_000), (F.synth_dense, 3000), (F.synth_dense, 1)):
+        p = gen(n)
+        for x in (p, p.astype(np.float16)):
+            boxes, cnt = yu.decode_nms(x, 20, 2)
+            rows, cnt2 = yu.decode_nms(x, 20, 2, compact=True)
+            assert np.array_equal(cnt2, cnt) and rows.shape == (int(cnt.sum()), 7)
+            m = np.arange(49)[None, :] < cnt[:, None]
+            assert np.array_equal(rows[:, 1:], boxes[m])
+            assert np.array_equal(rows[:, 0], np.repeat(np.arange(n, dtype=np.float32), cnt))
+    with pytest.raises(ValueError):
+        yu.decode_nms(_cuda(F.synth_dense(4), dev), 20, 2, compact=True)
+
+
 def test_decode_nms_large_vs_cport_and_properties(dev):
     """100k images against the C port; size-independent properties on the same output."""
     from yolohot import utils as yu
