@@ -35,6 +35,17 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// Programmatic dependent launch: launched with cudaLaunchAttributeProgrammaticStreamSerialization, a kernel's CTAs may be
+// scheduled while the kernel before it in the stream is still draining; griddepcontrol.wait then blocks until that kernel
+// has completed and its writes are visible, and is the first thing each thread does - before any global access - so the
+// stream's ordering is unchanged and only launch latency / CTA start-up overlap the predecessor's tail.  Both instructions
+// are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait_then_release()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
 // Box / confidence terms of one "heavy" cell (object, or a non-zero true box) and their gradients.  t, p: the cell's
@@ -223,6 +234,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
                                                             float *__restrict__ out_terms)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    pdl_wait_then_release();
     const int C = cfg.C, D = cfg.D;
     const int tile_fl = cfg.tile_cells * D;
     const uint32_t tile_bytes = static_cast<uint32_t>(tile_fl) * 4u;
@@ -400,6 +412,7 @@ __global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float
 {
     __shared__ int heavy[kGatherTile];
     __shared__ int wcount[kGatherCPT][kGatherThreads / 32];
+    pdl_wait_then_release();
     const int C = cfg.C, D = cfg.D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int nwarp = kGatherThreads / 32;
@@ -495,15 +508,22 @@ struct LossScratch {
     double *partials = nullptr;
     unsigned *ticket = nullptr;
     int cap_blocks = 0;
-    cudaEvent_t ev = nullptr;
+    cudaEvent_t ev = nullptr;         // recorded only when the scratch changes hands between streams
     cudaStream_t last = nullptr;
     bool used = false;
+};
+constexpr int kLossStreams = 8;       // streams per device with a scratch block of their own (no cross-stream ordering needed)
+struct LossStreamSlot {
+    cudaStream_t st = nullptr;
+    bool taken = false;
+    LossScratch sc;
 };
 struct LossGeo {
     size_t smem = 0;
     int per_sm = 0;
 };
-static LossScratch g_loss[64];
+static LossScratch g_loss[64];                     // shared fall-back once a device has used more than kLossStreams streams
+static LossStreamSlot g_loss_slot[64][kLossStreams];
 static LossGeo g_geo[4][64];
 static std::mutex g_loss_mu;
 
@@ -567,7 +587,27 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
     }
     const int grid = static_cast<int>(
         std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * (gather ? g.per_sm : std::min(g.per_sm, std::max(1, env_ctas))))));
-    LossScratch &sc = g_loss[dev];
+    // every stream gets its own partials / ticket (launches of one stream are ordered anyway, so nothing has to be
+    // recorded or waited for between them); only past kLossStreams streams per device is one block shared through an event
+    LossScratch *scp = nullptr;
+    bool shared = false;
+    for (int i = 0; i < kLossStreams && !scp; ++i) {
+        LossStreamSlot &sl = g_loss_slot[dev][i];
+        if (sl.taken && sl.st == st) scp = &sl.sc;
+    }
+    for (int i = 0; i < kLossStreams && !scp; ++i) {
+        LossStreamSlot &sl = g_loss_slot[dev][i];
+        if (!sl.taken) {
+            sl.taken = true;
+            sl.st = st;
+            scp = &sl.sc;
+        }
+    }
+    if (!scp) {
+        scp = &g_loss[dev];
+        shared = true;
+    }
+    LossScratch &sc = *scp;
     if (sc.cap_blocks < grid) {
         if (sc.partials) {
             YH_CUDA(cudaDeviceSynchronize());
@@ -580,12 +620,23 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
         YH_CUDA(cudaMemset(sc.ticket, 0, sizeof(unsigned)));
         YH_CUDA(cudaDeviceSynchronize());
         sc.cap_blocks = cap;
-        if (!sc.ev) YH_CUDA(cudaEventCreateWithFlags(&sc.ev, cudaEventDisableTiming));
+        if (shared && !sc.ev) YH_CUDA(cudaEventCreateWithFlags(&sc.ev, cudaEventDisableTiming));
     }
-    if (sc.used && sc.last != st) YH_CUDA(cudaStreamWaitEvent(st, sc.ev, 0));
-    kern<<<grid, threads, smem, st>>>(y_true, y_pred, cfg, out_grad, sc.partials, sc.ticket, out_terms);
+    if (shared && sc.used && sc.last != st) YH_CUDA(cudaStreamWaitEvent(st, sc.ev, 0));
+    static const bool pdl = [] { const char *v = getenv("YH_PDL"); return !(v && *v && atoi(v) == 0); }();
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(threads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = pdl ? 1 : 0;
+    YH_CUDA(cudaLaunchKernelEx(&lc, kern, y_true, y_pred, cfg, out_grad, sc.partials, sc.ticket, out_terms));
     YH_LAUNCH_CHECK("loss_kernel");
-    YH_CUDA(cudaEventRecord(sc.ev, st));
+    if (shared) YH_CUDA(cudaEventRecord(sc.ev, st));
     sc.used = true;
     sc.last = st;
     return YH_OK;

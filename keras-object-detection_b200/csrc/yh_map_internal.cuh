@@ -50,6 +50,11 @@ struct ReduceArgs {
     unsigned long long wait_epoch;
     long long wait_cycles;
     int32_t *err;                               // nullable device int: YH_MAP_ERR_* of the last failure
+    // counting path (YH_RADIX_AP): AP from ranks counted inside (class, confidence bucket) groups instead of a sort
+    int count_nb_log2;                          // log2 of the confidence buckets per class, -1 = path disabled
+    long long count_n_max;                      // taken when the DEVICE-side record count is <= this ...
+    unsigned long long count_pairs_max;
+    unsigned long long *dbg;         // ... and the pair count known after the histogram is <= this
 };
 
 size_t radix_ws_bytes(int64_t n_max, int C);

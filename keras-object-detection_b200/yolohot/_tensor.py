@@ -49,6 +49,8 @@ def ptr(h):
 def as_device_f32(x, device=None):
     """Any array-like -> (contiguous float32 CUDA torch tensor, kind) where kind tells the
     caller what to hand back: 'torch', 'numpy' (host array-likes) or 'tf'."""
+    if type(x) is torch.Tensor and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous():
+        return x, "torch"                # the common case of a device pipeline: nothing to do
     require_cuda()
     if isinstance(x, torch.Tensor):
         kind = "torch"
@@ -78,7 +80,7 @@ def head_to_f32(t):
     t = t.contiguous()
     out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
     code = _lib.YH_DTYPE_F16 if t.dtype == torch.float16 else _lib.YH_DTYPE_BF16
-    with torch.cuda.device(t.device):
+    with on_device(t.device):
         _lib.check(_lib.lib().yh_head_to_f32(t.data_ptr(), code, t.numel(), out.data_ptr(), stream_ptr(t.device)),
                    "head_to_f32")
     return out
@@ -110,5 +112,33 @@ def give_back(t, kind):
     return t
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device):
+    """cudaStream_t of torch's current stream on `device` (the raw getter when this torch has it: a tenth of the cost of
+    building a torch.cuda.Stream object - four of these per evaluator pass were a quarter of its host time)."""
+    if _raw_stream is not None:
+        idx = device.index if isinstance(device, torch.device) else device
+        return C.c_void_p(_raw_stream(torch.cuda.current_device() if idx is None else idx))
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class on_device:
+    """`with torch.cuda.device(dev)` that does nothing when dev already is the current device (the usual case)."""
+    __slots__ = ("dev", "ctx")
+
+    def __init__(self, dev):
+        self.dev, self.ctx = dev, None
+
+    def __enter__(self):
+        idx = self.dev.index if isinstance(self.dev, torch.device) else self.dev
+        if idx is not None and idx != torch.cuda.current_device():
+            self.ctx = torch.cuda.device(idx)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._tensor import require_cuda, stream_ptr
+from ._tensor import on_device, require_cuda, stream_ptr
 
 __all__ = ["get_boxes", "get_labels", "encode_labels", "YoloV1Labels"]
 
@@ -58,7 +58,7 @@ def encode_labels(boxes, offsets=None, grid=7, num_classes=20, num_boxes=2, devi
     elif tuple(out.shape) != (n, S, S, C + 5 * B) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("encode_labels: `out` must be a contiguous float32 (N, S, S, C+5B) tensor")
     bad = torch.zeros((1,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         _lib.check(_lib.lib().yh_encode_labels(b_d.data_ptr(), o_d.data_ptr(), n, S, B, C, out.data_ptr(),
                                                bad.data_ptr(), stream_ptr(dev)), "encode_labels")
     if check:

@@ -20,6 +20,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from ._tensor import on_device
+
 
 def world_size(group=None):
     return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -93,7 +95,7 @@ class PeerExchange:
         h = (C.c_ubyte * self._lib.YH_IPC_HANDLE_BYTES)()
         p = C.c_void_p()
         err = None
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             try:
                 self._lib.check(L.yh_ipc_alloc(nbytes, C.byref(p), h), "ipc_alloc")       # zero-filled
             except (RuntimeError, ValueError) as e:
@@ -145,7 +147,7 @@ class PeerExchange:
         ap = torch.empty((self.num_classes,), dtype=torch.float32, device=dev)
         m = torch.empty((1,), dtype=torch.float32, device=dev)
         ba = (C.c_void_p * self.world)(*self.bufs)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             sp = stream_ptr(dev)
             self._lib.check(L.yh_map_exchange(self.world, self.rank, ba, self.num_classes, self.capacity, rec.data_ptr(), n_max,
                                               nrec_dev.data_ptr() if nrec_dev is not None else None, gt_per_class.data_ptr(),
@@ -180,7 +182,7 @@ def peer_exchange(device, num_classes, n_bound, group=None, capacity=None):
           and dist.get_world_size(group) <= 16)
     if ok:
         info = [None] * dist.get_world_size(group)
-        with torch.cuda.device(device):
+        with on_device(device):
             dist.all_gather_object(info, (socket.gethostname(), int(capacity) if capacity else 4 * int(n_bound)), group=group)
         if len({h for h, _ in info}) == 1:
             cap = max(max(c for _, c in info), 1 << 16)

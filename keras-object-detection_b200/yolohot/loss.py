@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._tensor import DL, as_device_f32, dl, give_back, ptr, stream_ptr
+from ._tensor import DL, as_device_f32, dl, give_back, on_device, ptr, stream_ptr
 
 try:                                          # the reference's host framework, when it is there
     import tensorflow as _tf
@@ -39,7 +39,7 @@ def _run(y_true, y_pred, C, B, lc, ln, want_grad):
     dev = y_pred.device
     terms = torch.empty((6,), dtype=torch.float32, device=dev)
     grad = torch.empty_like(y_pred) if want_grad else None
-    with torch.cuda.device(dev):
+    with on_device(dev):
         ht, hp, ho, hg = DL(y_true), DL(y_pred), DL(terms), dl(grad)
         _lib.check(_lib.lib().yh_loss_dl(ht.ptr, hp.ptr, B, C, float(lc), float(ln), ho.ptr, ptr(hg), stream_ptr(dev)),
                    "YoloV1Loss")

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._tensor import DL, as_device_f32, as_grid, dl, give_back, ptr, require_cuda, stream_ptr
+from ._tensor import DL, as_device_f32, as_grid, dl, give_back, on_device, ptr, require_cuda, stream_ptr
 
 __all__ = [
     "intersection_over_union", "intersection_over_union_numpy",
@@ -45,7 +45,7 @@ def intersection_over_union(boxes1, boxes2):
     if a.shape[-1] != 4:
         raise ValueError(f"intersection_over_union: last dimension must be 4, got {tuple(a.shape)}")
     out = torch.empty(a.shape[:-1] + (1,), dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
+    with on_device(a.device):
         ha, hb, ho = DL(a), DL(b), DL(out)
         _lib.check(_lib.lib().yh_iou_dl(ha.ptr, hb.ptr, ho.ptr, stream_ptr(a.device)), "intersection_over_union")
     return give_back(out, kind)
@@ -64,7 +64,7 @@ def decode_predictions(predictions, num_classes, num_boxes=2, grid=None):
     p, kind = as_device_f32(predictions)
     p, n, S = as_grid(p, num_classes, num_boxes, grid)
     out = torch.empty((n, S * S, 6), dtype=torch.float32, device=p.device)
-    with torch.cuda.device(p.device):
+    with on_device(p.device):
         hp, ho = DL(p), DL(out)
         _lib.check(_lib.lib().yh_decode_dl(hp.ptr, int(num_boxes), int(num_classes), ho.ptr, stream_ptr(p.device)),
                    "decode_predictions")
@@ -91,7 +91,7 @@ def _nms_device(b, iou_threshold, conf_threshold, want_idx=False):
     out = torch.empty((n, M, 6), dtype=torch.float32, device=b.device)      # rows past count[i] are never handed out
     cnt = torch.empty((n,), dtype=torch.int32, device=b.device)
     kidx = torch.full((n, M), -1, dtype=torch.int32, device=b.device) if want_idx else None
-    with torch.cuda.device(b.device):
+    with on_device(b.device):
         hb, ho, hc, hk = DL(b), DL(out), DL(cnt), dl(kidx)
         _lib.check(_lib.lib().yh_nms_dl(hb.ptr, float(iou_threshold), float(conf_threshold), ho.ptr, hc.ptr, ptr(hk),
                                         stream_ptr(b.device)), "non_max_suppression")
@@ -216,7 +216,7 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
         boxes = torch.empty((n, S * S, 6), dtype=torch.float32, device=p.device)
         cnt = torch.empty((n,), dtype=torch.int32, device=p.device)
         kidx = torch.empty((n, S * S), dtype=torch.int32, device=p.device) if return_index else None
-    with torch.cuda.device(p.device):
+    with on_device(p.device):
         if half:
             code = _lib.YH_DTYPE_F16 if p.dtype == torch.float16 else _lib.YH_DTYPE_BF16
             _lib.check(L.yh_decode_nms_typed(p.data_ptr(), code, n, S, int(num_boxes), int(num_classes), float(iou_threshold),
@@ -224,9 +224,12 @@ def decode_nms(predictions, num_classes, num_boxes=2, iou_threshold=0.5, conf_th
                                              cnt.data_ptr(), kidx.data_ptr() if kidx is not None else None,
                                              stream_ptr(p.device)), "decode_nms")
         elif score_mode == "conf":
-            hp, hb, hc, hk = DL(p), DL(boxes), DL(cnt), dl(kidx)
-            _lib.check(L.yh_decode_nms_dl(hp.ptr, int(num_boxes), int(num_classes), float(iou_threshold),
-                                          float(conf_threshold), hb.ptr, hc.ptr, ptr(hk), stream_ptr(p.device)), "decode_nms")
+            # raw pointers: everything the DLPack front end (yh_decode_nms_dl) would check has been checked above -
+            # as_device_f32 / as_grid for the input, the block above (or the allocation) for the outputs - and three
+            # capsules per call were a fifth of an evaluator pass's host time
+            _lib.check(L.yh_decode_nms(p.data_ptr(), n, S, int(num_boxes), int(num_classes), float(iou_threshold),
+                                       float(conf_threshold), boxes.data_ptr(), cnt.data_ptr(),
+                                       kidx.data_ptr() if kidx is not None else None, stream_ptr(p.device)), "decode_nms")
         else:
             _lib.check(L.yh_decode_nms_ex(p.data_ptr(), n, S, int(num_boxes), int(num_classes), float(iou_threshold),
                                           float(conf_threshold), 1, boxes.data_ptr(), cnt.data_ptr(),
@@ -258,7 +261,7 @@ def map_match(true_rows, pred_rows, num_classes, iou_threshold=0.5, rows_by_imag
     nt, npred = int(t.shape[0]), int(p.shape[0])
     rec = torch.empty((npred,), dtype=torch.int64, device=dev)
     gtc = torch.empty((num_classes,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         _lib.check(_lib.lib().yh_map_match(t.data_ptr(), nt, None, p.data_ptr(), npred, None, int(num_classes),
                                            float(iou_threshold), _lib.YH_MAP_TRUE_ROWS_BY_IMAGE if rows_by_image else 0,
                                            rec.data_ptr(), gtc.data_ptr(), None, 0, stream_ptr(dev)), "map_match")
@@ -272,7 +275,7 @@ def map_reduce(rec, gt_per_class, num_classes, nrec_dev=None, workspace=None, n_
     dev = gt_per_class.device
     ap = torch.empty((num_classes,), dtype=torch.float32, device=dev)
     m = torch.empty((1,), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         _lib.check(_lib.lib().yh_map_reduce(rec.data_ptr(), int(rec.shape[0]), nrec_dev.data_ptr() if nrec_dev is not None else None,
                                             int(n_hint), gt_per_class.data_ptr(), int(num_classes), ap.data_ptr(), m.data_ptr(),
                                             workspace.data_ptr() if workspace is not None else None,
@@ -443,7 +446,7 @@ class MeanAveragePrecision:
             tb, tc = decode_nms(yt, self._num_classes, self._num_boxes, 0.5, 0.4, out=(bufs[2], bufs[3]))
         else:                                       # stale metric.py:81: conf > 0.4 only, cell order
             tb, tc = _filter_rows(decode_predictions(yt, self._num_classes, self._num_boxes), 0.4)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             _lib.check(_lib.lib().yh_eval_update(pb.data_ptr(), pc.data_ptr(), tb.data_ptr(), tc.data_ptr(), n, M, int(self.img_idx),
                                                  self._num_classes, self._IOU_THR, st["pred"].data_ptr(), st["cap"],
                                                  st["true"].data_ptr(), st["cap"], st["rec"].data_ptr(), st["cursors"].data_ptr(),
@@ -487,7 +490,7 @@ def _filter_rows(boxes, conf_threshold):
     n, M = int(boxes.shape[0]), int(boxes.shape[1])
     out = torch.empty((n, M, 6), dtype=torch.float32, device=boxes.device)
     cnt = torch.empty((n,), dtype=torch.int32, device=boxes.device)
-    with torch.cuda.device(boxes.device):
+    with on_device(boxes.device):
         _lib.check(_lib.lib().yh_filter_rows(boxes.data_ptr(), n, M, float(conf_threshold), out.data_ptr(), cnt.data_ptr(),
                                              stream_ptr(boxes.device)), "filter_rows")
     return out, cnt
@@ -514,7 +517,7 @@ def pixel_boxes(boxes, width, height, count=None):
         if cnt.numel() != n:
             raise ValueError("pixel_boxes: count must hold one entry per image")
     if n * M:
-        with torch.cuda.device(b.device):
+        with on_device(b.device):
             _lib.check(_lib.lib().yh_pixel_boxes(b3.data_ptr(), cnt.data_ptr() if cnt is not None else None, n, M,
                                                  int(width), int(height), out.data_ptr(), stream_ptr(b.device)),
                        "pixel_boxes")

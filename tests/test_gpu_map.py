@@ -77,6 +77,55 @@ def test_radix_reduce_vs_numpy(dev, n, C, quant):
     assert torch.equal(ap2, ap) and torch.equal(m2, m)
 
 
+@pytest.mark.parametrize("n,C,quant,skew", [(0, 3, 0, 0.0), (1, 1, 0, 0.0), (5000, 20, 0, 0.0), (73_595, 20, 0, 0.0), (73_595, 20, 16, 0.5),
+                                            (200_000, 80, 0, 0.0), (150_000, 512, 3, 0.0), (400_000, 20, 0, 0.9), (30_000, 1, 0, 0.0)])
+def test_counting_path_equals_radix_path(dev, n, C, quant, skew, monkeypatch):
+    """The sort-free AP (ranks counted inside (class, confidence bucket) groups) against the radix-sort path on the same
+    records: AP per class and mAP bit for bit - for continuous and tie-heavy confidences, confidences outside [0, 1],
+    infinities and NaNs (which have a place in the sort order), a dominant class, one bucket per class, and the fall-back
+    to the radix passes when the pair count known after the histogram is over the limit."""
+    from yolohot import utils as yu
+    rng = np.random.default_rng(7 * n + C)
+    cls = rng.integers(0, C + 1, n)
+    if skew:
+        cls[rng.random(n) < skew] = C // 2
+    conf = rng.random(n).astype(F32)
+    if quant:
+        conf = (np.floor(conf * quant) / quant).astype(F32)
+    odd = rng.random(n)
+    conf[odd < 0.01] = 0.0
+    conf[(odd >= 0.01) & (odd < 0.02)] = 1.0
+    conf[(odd >= 0.02) & (odd < 0.025)] = -0.25
+    conf[(odd >= 0.025) & (odd < 0.03)] = 1.75
+    conf[(odd >= 0.03) & (odd < 0.032)] = np.inf
+    conf[(odd >= 0.032) & (odd < 0.034)] = -np.inf
+    conf[(odd >= 0.034) & (odd < 0.036)] = np.nan
+    conf[(odd >= 0.036) & (odd < 0.038)] = -np.nan
+    tp = (rng.random(n) < 0.35).astype(np.uint8)
+    tp[cls == C] = 0
+    gt = rng.integers(0, 50, C).astype(np.int32) + np.bincount(cls[tp == 1], minlength=C + 1)[:C].astype(np.int32)
+    if C > 2:
+        gt[rng.random(C) < 0.1] = 0
+    rec = torch.from_numpy(_pack(cls, conf, tp).view(np.int64)).to(dev)
+    gtd = torch.from_numpy(gt).to(dev)
+
+    def run(**env):
+        for k in ("YH_MAP_COUNT", "YH_MAP_COUNT_PAIRS", "YH_MAP_COUNT_BUCKETS", "YH_MAP_COUNT_NMAX"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, str(v))
+        m, ap = yu.map_reduce(rec, gtd, C)
+        torch.cuda.synchronize()
+        return m.clone(), ap.clone()
+
+    m0, ap0 = run(YH_MAP_COUNT=0)                                     # radix passes only
+    for env in ({}, {"YH_MAP_COUNT_BUCKETS": 1}, {"YH_MAP_COUNT_BUCKETS": 4}, {"YH_MAP_COUNT_PAIRS": 1},
+                {"YH_MAP_COUNT_PAIRS": 10**15, "YH_MAP_COUNT_NMAX": 10**9}):
+        m1, ap1 = run(**env)
+        assert torch.equal(ap1.view(torch.int32), ap0.view(torch.int32)), env
+        assert torch.equal(m1.view(torch.int32), m0.view(torch.int32)), env
+
+
 def test_rows_append_chained_scan(dev):
     """yh_rows_append / yh_eval_update row buffers against a NumPy compaction, from one tile to a thousand."""
     from yolohot import _lib
