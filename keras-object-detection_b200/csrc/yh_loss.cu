@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "yh_common.cuh"
 
@@ -45,6 +46,20 @@ __device__ __forceinline__ void pdl_wait_then_release()
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+
+#ifdef YH_LOSS_TIMELINE
+__device__ unsigned long long g_loss_tl[8][2048];
+#define LOSS_STAMP(k)                                                                         \
+    do {                                                                                      \
+        if (threadIdx.x == 0 && blockIdx.x < 2048) {                                          \
+            unsigned long long t_;                                                            \
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)::"memory");                   \
+            g_loss_tl[k][blockIdx.x] = t_;                                                    \
+        }                                                                                     \
+    } while (0)
+#else
+#define LOSS_STAMP(k)
+#endif
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
@@ -137,7 +152,7 @@ __device__ __forceinline__ void heavy_class_term(const float *t, const float *p,
 
 // Deterministic batch sums: lanes -> warp -> block partials (fixed order); the last block to finish (ticket counter)
 // adds the partials of all blocks in index order and writes the six outputs, so the result does not depend on which
-// block came last.  Called by every thread of the block (>= 128 threads), once.
+// block came last.  Called by every thread of the block (whole warps, at most kLossMaxWarps), once.
 constexpr int kLossMaxWarps = 8;
 __device__ __forceinline__ void block_finish(double sxy, double swh, double sob, double snb, double scl, const LossCfg &cfg,
                                              double *__restrict__ partials, unsigned *__restrict__ ticket,
@@ -158,10 +173,12 @@ __device__ __forceinline__ void block_finish(double sxy, double swh, double sob,
         for (int w = 0; w < nwarp; ++w) s += red[w][threadIdx.x];
         partials[static_cast<size_t>(blockIdx.x) * 5 + threadIdx.x] = s;
     }
-    // stage 2: the last block (ticket) sums all partials in block-index order
-    __threadfence();
+    // stage 2: the last block (ticket) sums all partials in block-index order.  Barrier, then ONE thread fences and takes
+    // the ticket: its fence is cumulative over the partials the barrier ordered before it, and the other 100+ threads
+    // no longer wait for their own gradient stores to drain before the block may leave
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         const unsigned prev = atomicAdd(ticket, 1u);
         is_last = (prev == gridDim.x - 1);
     }
@@ -172,14 +189,15 @@ __device__ __forceinline__ void block_finish(double sxy, double swh, double sob,
     // The loads of a thread are issued together (one L2 round trip, not one per block) and added in
     // block order afterwards.
     const int term = threadIdx.x % 5, slot = threadIdx.x / 5;
-    if (slot < 25) {
+    const int nslot = min(25, static_cast<int>(blockDim.x) / 5);              // 25 for blocks of >= 125 threads
+    if (slot < nslot) {
         double s = 0;
         const int nb = static_cast<int>(gridDim.x);
-        for (int b0 = slot; b0 < nb; b0 += 25 * 16) {
+        for (int b0 = slot; b0 < nb; b0 += nslot * 16) {
             double v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const int b = b0 + 25 * j;
+                const int b = b0 + nslot * j;
                 v[j] = (b < nb) ? __ldcg(partials + static_cast<size_t>(b) * 5 + term) : 0.0;
             }
 #pragma unroll
@@ -190,7 +208,7 @@ __device__ __forceinline__ void block_finish(double sxy, double swh, double sob,
     __syncthreads();
     if (threadIdx.x < 5) {
         double tot = 0;
-        for (int i = 0; i < 25; ++i) tot += fin[threadIdx.x][i];
+        for (int i = 0; i < nslot; ++i) tot += fin[threadIdx.x][i];
         fin[threadIdx.x][25] = tot;
         out_terms[threadIdx.x] = static_cast<float>(tot);
     }
@@ -403,16 +421,23 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
 constexpr int kGatherThreads = YH_GATHER_THREADS;
 constexpr int kGatherCPT = YH_GATHER_CPT;                       // cells per thread: fewer, fatter threads keep a cfg3-sized batch in ONE wave
 constexpr int kGatherTile = kGatherThreads * kGatherCPT;
+constexpr int kZeroFloats = 4096;                               // 16 KB of zeros for the bulk zero fill of the gradient tiles
 
 template <bool kGrad>
-__global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
+__global__ void __launch_bounds__(kGatherThreads, 3) loss_gather_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
                                                                      LossCfg cfg, float *__restrict__ grad,
                                                                      double *__restrict__ partials, unsigned *__restrict__ ticket,
                                                                      float *__restrict__ out_terms)
 {
     __shared__ int heavy[kGatherTile];
     __shared__ int wcount[kGatherCPT][kGatherThreads / 32];
+    // the gradient tile is zero-filled by the TMA engine from this block of zeros (cp.async.bulk shared -> global): threads
+    // that issue 24 MB of plain stores sit in the store queue for 4 - 9 us (timeline in profiles/README.md) before they can
+    // even look at the values they loaded; a bulk copy costs one thread a few instructions
+    __shared__ __align__(128) float zeros[kZeroFloats];
+    LOSS_STAMP(0);
     pdl_wait_then_release();
+    LOSS_STAMP(1);
     const int C = cfg.C, D = cfg.D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int nwarp = kGatherThreads / 32;
@@ -420,6 +445,12 @@ __global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float
     const bool gvec_ok = kGrad && (reinterpret_cast<uintptr_t>(grad) % 16 == 0) && ((static_cast<int64_t>(kGatherTile) * D) % 4 == 0);
     const bool pair_ok = (((C | D) & 1) == 0) && (reinterpret_cast<uintptr_t>(yt) % 8 == 0);   // y_true[C..C+3] as two aligned pairs
     double sxy = 0, swh = 0, sob = 0, snb = 0, scl = 0;
+    if (kGrad && gvec_ok) {
+        float4 *z4 = reinterpret_cast<float4 *>(zeros);
+        for (int i = threadIdx.x; i < kZeroFloats / 4; i += kGatherThreads) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_proxy_async_smem();                                             // generic-proxy writes -> visible to the TMA engine
+        __syncthreads();
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t cell0 = tile * kGatherTile;
         const int cells = static_cast<int>(min(static_cast<int64_t>(kGatherTile), cfg.n_cells - cell0));
@@ -448,13 +479,21 @@ __global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float
             float *gg = grad + cell0 * D;
             const int nfl = cells * D;
             if (gvec_ok && cells == kGatherTile) {
-                float4 *g4 = reinterpret_cast<float4 *>(gg);
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int i = threadIdx.x; i < (nfl >> 2); i += kGatherThreads) g4[i] = z;
+                if (threadIdx.x == 0) {                                       // nfl * 4 bytes in pieces of the zero block
+                    const uint32_t total = static_cast<uint32_t>(nfl) * 4u;
+                    for (uint32_t o = 0; o < total; o += kZeroFloats * 4u) {
+                        const uint32_t nbytes = min(static_cast<uint32_t>(kZeroFloats) * 4u, total - o);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<char *>(gg) + o),
+                                     "r"(smem_u32(zeros)), "r"(nbytes)
+                                     : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             } else {
                 for (int i = threadIdx.x; i < nfl; i += kGatherThreads) gg[i] = 0.f;
             }
         }
+        LOSS_STAMP(2);
         // ---- pass A: light cells, compaction of the heavy ones ----
         bool hv[kGatherCPT];
         float g_light[kGatherCPT];
@@ -472,7 +511,9 @@ __global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float
             bal[j] = __ballot_sync(0xffffffffu, hv[j]);
             if (lane == 0) wcount[j][warp] = __popc(bal[j]);
         }
+        if (kGrad && threadIdx.x == 0) bulk_store_wait_all();                 // the zero fill has been written (long ago: it was issued before the loads came back)
         __syncthreads();                                                      // also: zero fill before the stores below
+        LOSS_STAMP(3);
         int n_heavy = 0;
 #pragma unroll
         for (int j = 0; j < kGatherCPT; ++j) {
@@ -488,17 +529,202 @@ __global__ void __launch_bounds__(kGatherThreads) loss_gather_kernel(const float
             if (kGrad && in[j] && !hv[j]) grad[(cell0 + cell) * D + C] = g_light[j];
         }
         __syncthreads();                                                      // heavy[] complete
-        // ---- pass B: box / confidence terms of the heavy cells, thread per cell; pass C: class term, warp per cell ----
-        for (int h = threadIdx.x; h < n_heavy; h += kGatherThreads) {
-            const int64_t off = (cell0 + heavy[h]) * D;
-            heavy_box_terms<kGrad>(yt + off, yp + off, kGrad ? grad + off : nullptr, cfg, sxy, swh, sob, snb);
-        }
-        for (int h = warp; h < n_heavy; h += nwarp) {
-            const int64_t off = (cell0 + heavy[h]) * D;
-            heavy_class_term<kGrad>(yt + off, yp + off, kGrad ? grad + off : nullptr, C, lane, scl);
+        // ---- pass C first: class term of the heavy cells with an object (loss.py:206), flattened over (cell, class) so that
+        //      every thread has ALL its loads in flight at once - one L2 round trip for the CTA instead of one per cell and
+        //      warp (a warp-per-cell loop cost three to four dependent round trips: 3.5 of the kernel's 18 us) - and they fly
+        //      while pass B (box / confidence terms, thread per heavy cell: IoUs, square roots, divisions) computes ----
+        constexpr int CI = 4;                                                 // (cell, class) items per thread and batch
+        const int n_items = n_heavy * C;
+        const int n_batches = max((n_items + CI * kGatherThreads - 1) / (CI * kGatherThreads), (n_heavy + kGatherThreads - 1) / kGatherThreads);
+        const int sh = kGatherThreads / C, sj = kGatherThreads % C;
+        int ih = threadIdx.x / C, ij = threadIdx.x % C;                       // item tid + k * 256 = (heavy cell ih, class ij)
+        for (int b = 0; b < n_batches; ++b) {
+            float to[CI], tj[CI], pj[CI];
+            int64_t go[CI];
+#pragma unroll
+            for (int q = 0; q < CI; ++q) {
+                go[q] = -1;
+                to[q] = tj[q] = pj[q] = 0.f;
+                if ((b * CI + q) * kGatherThreads + static_cast<int>(threadIdx.x) < n_items) {
+                    const int64_t off = (cell0 + heavy[ih]) * D;
+                    to[q] = __ldg(yt + off + C);
+                    tj[q] = __ldg(yt + off + ij);
+                    pj[q] = __ldg(yp + off + ij);
+                    go[q] = off + ij;
+                }
+                ih += sh;
+                ij += sj;
+                if (ij >= C) { ij -= C; ++ih; }
+            }
+            const int h = b * kGatherThreads + static_cast<int>(threadIdx.x);   // pass B: thread per heavy cell
+            if (h < n_heavy) {
+                const int64_t off = (cell0 + heavy[h]) * D;
+                heavy_box_terms<kGrad>(yt + off, yp + off, kGrad ? grad + off : nullptr, cfg, sxy, swh, sob, snb);
+            }
+#pragma unroll
+            for (int q = 0; q < CI; ++q) {
+                if (go[q] >= 0 && to[q] != 0.0f) {
+                    const float d = __fsub_rn(tj[q], pj[q]);
+                    scl += static_cast<double>(__fmul_rn(to[q], __fmul_rn(d, d)));
+                    if (kGrad) grad[go[q]] = -2.0f * to[q] * d;
+                }
+            }
         }
         if (tile + gridDim.x < n_tiles) __syncthreads();                      // heavy[] / wcount[] are reused by the next tile
     }
+    LOSS_STAMP(4);
+    block_finish(sxy, swh, sob, snb, scl, cfg, partials, ticket, out_terms);
+    LOSS_STAMP(5);
+}
+
+// ------------------------------------------------------------------------------------------
+// Stream variant (mid-size batches, cfg3): TMA in, TMA out, nothing else touches global memory.
+// What the per-CTA timeline of the gather kernel showed at cfg3 (profiles/README.md): its 4-byte gathers are bound by the
+// SM's miss tracking (threads spend 4 - 9 us just ISSUING their loads), and everything that needs a second look at
+// memory - the full rows of the heavy cells - queues behind the whole backlog (3 - 4 us).  Here a tile of 64 cells (both
+// tensors, 2 x 7,680 B) arrives by cp.async.bulk into a 2-stage ring (as in loss_kernel), thread = cell works on it in
+// shared memory - the heavy cells' rows are already there, so there is no second round trip and no deferral list - and
+// the gradient tile is COMPOSED in shared memory (zeros + the few non-zero entries) and leaves as one bulk store
+// (cp.async.bulk shared -> global): no zero-fill stores through the LSU, no ordering between a fill and the sparse
+// writes.  Small CTAs (2 warps, 4 per SM) keep the three barriers of a tile cheap and 60 - 120 KB per SM in flight.
+// Bit-identical gradients and per-cell terms to the other two kernels (same device functions).
+// ------------------------------------------------------------------------------------------
+constexpr int kStreamThreads = 64;                              // = cells per tile
+constexpr int kStreamStages = 2;
+
+template <bool kGrad>
+__global__ void __launch_bounds__(kStreamThreads) loss_stream_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
+                                                                     LossCfg cfg, float *__restrict__ grad,
+                                                                     double *__restrict__ partials, unsigned *__restrict__ ticket,
+                                                                     float *__restrict__ out_terms)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int wcount[kStreamThreads / 32];
+    pdl_wait_then_release();
+    constexpr int TT = kStreamThreads;
+    const int C = cfg.C, D = cfg.D;
+    const int tile_fl = TT * D;
+    const uint32_t tile_bytes = static_cast<uint32_t>(tile_fl) * 4u;                 // 256 * D: a multiple of 16
+    float *ring = reinterpret_cast<float *>(smem);                                    // [stage][y_true tile | y_pred tile]
+    float *gbuf = ring + static_cast<size_t>(kStreamStages) * 2 * tile_fl;            // [2][tile] gradient tiles (double buffered)
+    uint64_t *full = reinterpret_cast<uint64_t *>(gbuf + 2 * static_cast<size_t>(tile_fl));
+    int *heavy = reinterpret_cast<int *>(full + kStreamStages);                       // [TT]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (cfg.n_cells + TT - 1) / TT;
+    const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool in_ok = ((reinterpret_cast<uintptr_t>(yt) | reinterpret_cast<uintptr_t>(yp)) % 16 == 0);
+    const bool out_ok = kGrad && (reinterpret_cast<uintptr_t>(grad) % 16 == 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStreamStages; ++s) mbar_init(full + s, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto cells_of = [&](int64_t it) {
+        const int64_t cell0 = (blockIdx.x + it * gridDim.x) * TT;
+        return static_cast<int>(min(static_cast<int64_t>(TT), cfg.n_cells - cell0));
+    };
+    auto issue = [&](int64_t it) {       // thread 0 only; full, aligned tiles
+        const int s = static_cast<int>(it % kStreamStages);
+        const int64_t off = (blockIdx.x + it * gridDim.x) * static_cast<int64_t>(tile_fl);
+        mbar_arrive_expect_tx(full + s, 2 * tile_bytes);
+        const uint64_t pol = l2_evict_first_policy();
+        bulk_g2s(ring + static_cast<size_t>(s) * 2 * tile_fl, yt + off, tile_bytes, full + s, pol);
+        bulk_g2s(ring + static_cast<size_t>(s) * 2 * tile_fl + tile_fl, yp + off, tile_bytes, full + s, pol);
+    };
+    if (threadIdx.x == 0 && my_tiles > 0 && in_ok && cells_of(0) == TT) issue(0);
+    if (kGrad) {                                                                      // both gradient tiles start as zeros
+        float4 *g4 = reinterpret_cast<float4 *>(gbuf);
+        for (int i = threadIdx.x; i < (2 * tile_fl) >> 2; i += TT) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double sxy = 0, swh = 0, sob = 0, snb = 0, scl = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int s = static_cast<int>(it % kStreamStages);
+        const uint32_t ph = static_cast<uint32_t>((it / kStreamStages) & 1);
+        const int64_t cell0 = (blockIdx.x + it * gridDim.x) * TT;
+        const int cells = cells_of(it);
+        float *st = ring + static_cast<size_t>(s) * 2 * tile_fl;
+        float *sp = st + tile_fl;
+        float *gb = gbuf + static_cast<size_t>(it & 1) * tile_fl;
+        const bool bulk_in = in_ok && cells == TT;
+        // the other stage was read by tile it-1, which every thread left at the barrier that ends an iteration
+        if (threadIdx.x == 0 && it + 1 < my_tiles && in_ok && cells_of(it + 1) == TT) issue(it + 1);
+        if (kGrad && it >= 2) {
+            // this gradient buffer left with tile it-2: once the TMA engine has read it, make it zeros again
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+            float4 *g4 = reinterpret_cast<float4 *>(gb);
+            for (int i = threadIdx.x; i < tile_fl >> 2; i += TT) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (bulk_in) {
+            mbar_wait(full + s, ph);
+        } else {
+            const float *gt = yt + cell0 * D, *gp = yp + cell0 * D;
+            for (int i = threadIdx.x; i < cells * D; i += TT) {
+                st[i] = gt[i];
+                sp[i] = gp[i];
+            }
+            __syncthreads();
+        }
+        // ---- pass A: thread = cell; light cells owe the no-object term on box 0 (loss.py:136,197) ----
+        const int cell = threadIdx.x;
+        const bool in = cell < cells;
+        bool hv = false;
+        float g_light = 0.f;
+        if (in) {
+            const float *t = st + cell * D;
+            const float obj = t[C];
+            hv = (obj != 0.0f) || (t[C + 1] != 0.0f) || (t[C + 2] != 0.0f) || (t[C + 3] != 0.0f) || (t[C + 4] != 0.0f);
+            if (!hv) {
+                const float c = sp[cell * D + C];
+                const float noobj = __fsub_rn(1.0f, obj);                             // loss.py:163
+                const float z = __fsub_rn(0.0f, c);
+                snb += static_cast<double>(__fmul_rn(noobj, __fmul_rn(z, z)));        // loss.py:197
+                g_light = cfg.ln * 2.0f * noobj * c;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hv);
+        if (lane == 0) wcount[warp] = __popc(bal);
+        __syncthreads();                                                              // also: the zeros of gb are in place
+        int base = 0, n_heavy = 0;
+#pragma unroll
+        for (int w = 0; w < TT / 32; ++w) {
+            const int k = wcount[w];
+            base += (w < warp) ? k : 0;
+            n_heavy += k;
+        }
+        if (hv) heavy[base + __popc(bal & ((1u << lane) - 1u))] = cell;
+        if (kGrad && in && !hv) gb[cell * D + C] = g_light;
+        __syncthreads();                                                              // heavy[] complete
+        // ---- heavy cells (~5 %): class term flattened over (cell, class), box / confidence terms thread per cell - all
+        //      from the stage in shared memory, gradients into the tile in shared memory ----
+        for (int itx = threadIdx.x; itx < n_heavy * C; itx += TT) {
+            const int h = itx / C, j = itx - h * C;
+            const int hc = heavy[h];
+            const float obj = st[hc * D + C];
+            if (obj != 0.0f) {                                                        // loss.py:206
+                const float d = __fsub_rn(st[hc * D + j], sp[hc * D + j]);
+                scl += static_cast<double>(__fmul_rn(obj, __fmul_rn(d, d)));
+                if (kGrad) gb[hc * D + j] = -2.0f * obj * d;
+            }
+        }
+        if (static_cast<int>(threadIdx.x) < n_heavy) {
+            const int hc = heavy[threadIdx.x];
+            heavy_box_terms<kGrad>(st + hc * D, sp + hc * D, kGrad ? gb + hc * D : nullptr, cfg, sxy, swh, sob, snb);
+        }
+        // ---- the gradient tile leaves as one bulk store ----
+        const bool bulk_out = out_ok && cells == TT;
+        if (kGrad && bulk_out) fence_proxy_async_smem();                              // generic-proxy writes -> visible to the TMA engine
+        __syncthreads();                                                              // everybody is done with this stage, heavy[] and gb
+        if (kGrad) {
+            if (bulk_out) {
+                if (threadIdx.x == 0) bulk_s2g(grad + cell0 * D, gb, tile_bytes);
+            } else {
+                float *gg = grad + cell0 * D;                                         // ragged last tile, unaligned gradient
+                for (int i = threadIdx.x; i < cells * D; i += TT) gg[i] = gb[i];
+            }
+        }
+    }
+    if (kGrad && threadIdx.x == 0) bulk_store_wait_read_all();                        // shared memory must outlive the TMA reads
     block_finish(sxy, swh, sob, snb, scl, cfg, partials, ticket, out_terms);
 }
 
@@ -524,7 +750,7 @@ struct LossGeo {
 };
 static LossScratch g_loss[64];                     // shared fall-back once a device has used more than kLossStreams streams
 static LossStreamSlot g_loss_slot[64][kLossStreams];
-static LossGeo g_geo[4][64];
+static LossGeo g_geo[6][64];
 static std::mutex g_loss_mu;
 
 }  // namespace yh
@@ -564,20 +790,27 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
     // 131,072; with two cells per thread the cfg3 batch is a single wave of CTAs: 21.0 vs 21.8 us); YH_LOSS_GATHER = 0 / 1
     // forces one of them
     const char *gv = getenv("YH_LOSS_GATHER");                     // read per call: the tests switch it
-    const int env_gather = (gv && *gv) ? atoi(gv) : -1;
-    const bool gather = env_gather >= 0 ? env_gather != 0 : n_cells >= (1 << 16);
-    const int64_t n_tiles = gather ? (n_cells + kGatherTile - 1) / kGatherTile : (n_cells + tile - 1) / tile;
+    const int env_gather = (gv && *gv) ? atoi(gv) : -1;            // 0 = ring, 1 = gather, 2 = stream
+    const size_t smem_stream = static_cast<size_t>(kStreamStages * 2 + 2) * kStreamThreads * cfg.D * 4 + kStreamStages * 8 + kStreamThreads * 4 + 64;
+    // measured (B200, fwd+bwd us at batch 1,024 / 4,096 / 16,384 / 65,536): ring 11.3 / 20.5 / 57.4 / 196, gather 10.6 / 19.7 /
+    // 57.7 / 188, stream 11.4 / 20.2 / 52.2 / 179 (6.45 TB/s); forward only: gather 8.2 / 14.3 / 38.7 / 119 beats both
+    int which = env_gather >= 0 ? env_gather : (n_cells < (1 << 15) ? 0 : (out_grad && n_cells >= 393216) ? 2 : 1);
+    if (which == 2 && smem_stream > static_cast<size_t>(100) * 1024) which = 1;
+    const bool gather = which == 1, stream_k = which == 2;
+    const int64_t n_tiles = gather ? (n_cells + kGatherTile - 1) / kGatherTile
+                                   : stream_k ? (n_cells + kStreamThreads - 1) / kStreamThreads : (n_cells + tile - 1) / tile;
     auto kern = gather ? (out_grad ? loss_gather_kernel<true> : loss_gather_kernel<false>)
-                       : (out_grad ? loss_kernel<true> : loss_kernel<false>);
-    const size_t smem = gather ? 0 : smem_tma;
-    const int threads = gather ? kGatherThreads : kLossThreads;
+                       : stream_k ? (out_grad ? loss_stream_kernel<true> : loss_stream_kernel<false>)
+                                  : (out_grad ? loss_kernel<true> : loss_kernel<false>);
+    const size_t smem = gather ? 0 : stream_k ? smem_stream : smem_tma;
+    const int threads = gather ? kGatherThreads : stream_k ? kStreamThreads : kLossThreads;
 
     int dev = 0;
     YH_CUDA(cudaGetDevice(&dev));
     YH_REQUIRE(dev >= 0 && dev < 64, "loss: device index %d out of range", dev);
     std::lock_guard<std::mutex> lock(g_loss_mu);
     // launch geometry is cached: the attribute / occupancy queries cost more than the kernel
-    LossGeo &g = g_geo[(out_grad ? 1 : 0) + (gather ? 2 : 0)][dev];
+    LossGeo &g = g_geo[(out_grad ? 1 : 0) + 2 * which][dev];
     if (g.smem != smem || g.per_sm == 0) {
         if (smem) YH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         int per_sm = 1;
@@ -586,7 +819,7 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
         g.per_sm = per_sm < 1 ? 1 : per_sm;
     }
     const int grid = static_cast<int>(
-        std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * (gather ? g.per_sm : std::min(g.per_sm, std::max(1, env_ctas))))));
+        std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * ((gather || stream_k) ? g.per_sm : std::min(g.per_sm, std::max(1, env_ctas))))));
     // every stream gets its own partials / ticket (launches of one stream are ordered anyway, so nothing has to be
     // recorded or waited for between them); only past kLossStreams streams per device is one block shared through an event
     LossScratch *scp = nullptr;
@@ -636,6 +869,25 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
     lc.numAttrs = pdl ? 1 : 0;
     YH_CUDA(cudaLaunchKernelEx(&lc, kern, y_true, y_pred, cfg, out_grad, sc.partials, sc.ticket, out_terms));
     YH_LAUNCH_CHECK("loss_kernel");
+#ifdef YH_LOSS_TIMELINE
+    if (getenv("YH_LOSS_DBG") && gather) {
+        static unsigned long long h[8][2048];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_loss_tl, sizeof(h));
+        const int nb = std::min(grid, 2048);
+        unsigned long long t0 = ~0ull;
+        for (int b = 0; b < nb; ++b) t0 = std::min(t0, h[0][b]);
+        const char *nm[] = {"start", "pdl-wait", "loads+zero issued", "light done", "heavy done", "finish"};
+        fprintf(stderr, "loss timeline (us after the first CTA started; min / median / max over %d CTAs):", nb);
+        for (int k = 0; k < 6; ++k) {
+            std::vector<double> v;
+            for (int b = 0; b < nb; ++b) v.push_back((double)(h[k][b] - t0) / 1000.0);
+            std::sort(v.begin(), v.end());
+            fprintf(stderr, "  %s %.2f/%.2f/%.2f", nm[k], v.front(), v[v.size() / 2], v.back());
+        }
+        fprintf(stderr, "\n");
+    }
+#endif
     if (shared) YH_CUDA(cudaEventRecord(sc.ev, st));
     sc.used = true;
     sc.last = st;

@@ -1,3 +1,4 @@
+"""Phase timeline of the counting path of map_radix_kernel (build csrc/yh_map_reduce.cu with -DYH_MAP_TIMELINE, run with YH_MAP_DBG=1)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "keras-object-detection_b200"))
 import torch

@@ -293,7 +293,7 @@ def test_loss_reference_fixture_and_run_to_run(dev):
 
 
 def test_loss_kernels_agree(dev, monkeypatch):
-    """The two loss kernels (TMA ring, gather) against the oracle and each other: terms to 1e-5, gradients bit for bit
+    """The three loss kernels (TMA ring, gather, stream) against the oracle and each other: terms to 1e-5, gradients bit for bit
     (both evaluate the same per-cell closed form), on aligned, ragged and offset batches."""
     from yolohot import loss as yl
     for n, off in ((4096, 0), (777, 0), (130, 1), (1, 0)):
@@ -303,7 +303,7 @@ def test_loss_kernels_agree(dev, monkeypatch):
         p = _cuda(np.ascontiguousarray(yp), dev) if off == 0 else torch.from_numpy(F.synth_loss_pred((n + off, 7, 7, 30), seed=5)).to(dev)[off:]
         want = cport.loss(np.ascontiguousarray(yt), np.ascontiguousarray(yp), 20, 2)
         res = {}
-        for mode in ("0", "1"):
+        for mode in ("0", "1", "2"):                                  # TMA ring, gather, stream (TMA in / TMA out)
             monkeypatch.setenv("YH_LOSS_GATHER", mode)
             res[mode] = yl.yolo_v1_loss_terms(t, p, grad=True)
             np.testing.assert_allclose(res[mode][0].cpu().numpy(), want, rtol=1e-5, err_msg=f"n={n} off={off} gather={mode}")
@@ -311,7 +311,9 @@ def test_loss_kernels_agree(dev, monkeypatch):
             assert torch.equal(fwd, res[mode][0])
         monkeypatch.delenv("YH_LOSS_GATHER")
         assert torch.equal(res["0"][1], res["1"][1]), (n, off)
+        assert torch.equal(res["0"][1], res["2"][1]), (n, off)
         np.testing.assert_allclose(res["0"][0].cpu().numpy(), res["1"][0].cpu().numpy(), rtol=1e-6)
+        np.testing.assert_allclose(res["0"][0].cpu().numpy(), res["2"][0].cpu().numpy(), rtol=1e-6)
 
 
 def test_loss_linearity_property(dev):
