@@ -53,8 +53,9 @@ struct ReduceArgs {
     // counting path (YH_RADIX_AP): AP from ranks counted inside (class, confidence bucket) groups instead of a sort
     int count_nb_log2;                          // log2 of the confidence buckets per class, -1 = path disabled
     long long count_n_max;                      // taken when the DEVICE-side record count is <= this ...
-    unsigned long long count_pairs_max;
-    unsigned long long *dbg;         // ... and the pair count known after the histogram is <= this
+    unsigned long long count_pairs_max;         // ... and the pair count known after the histogram is <= this + count_pairs_per_rec * n
+    unsigned long long count_pairs_per_rec;
+    unsigned long long *dbg;                    // -DYH_MAP_TIMELINE: phase time stamps of CTA 0 (else null)
 };
 
 size_t radix_ws_bytes(int64_t n_max, int C);
