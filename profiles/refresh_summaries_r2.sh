@@ -10,7 +10,7 @@ cp gpurun_out/launches_r2_map.csv profiles/launches_r2_map_cfg4.csv
 cp gpurun_out/bench_r2_final.json profiles/bench_r2_final.json
 cp gpurun_out/bench_r2_ref.json profiles/bench_r2_reference_arm.json
 python profiles/launch_summary.py gpurun_out/launches_r2_final.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 2 --warmup 1 (YH_BENCH_SUSTAINED=20)" > profiles/launches_r2_final_summary.txt
-python profiles/launch_summary.py gpurun_out/launches_r2_map.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 200 python profiles/prof_map.py cfg4 (13 evaluator passes of 5,000 images: 4 launches each + 1 torch fill)" > profiles/launches_r2_map_cfg4_summary.txt
+python profiles/launch_summary.py gpurun_out/launches_r2_map.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 200 python profiles/prof_map.py cfg4 (13 evaluator passes of 5,000 images: 4 launches each + 1 torch fill; reduce on its counting path)" > profiles/launches_r2_map_cfg4_summary.txt
 A=$(ln "A': compaction of the survivors"); B=$(ln "B: stable descending rank (utils.py:98): r ="); T=$(ln "a duplicate rank <=> equal confidences"); K=$(ln "class key: the class id itself")
 C=$(ln "C: same-class masks.  Slot t"); D=$(ln "D: suppression bits against same-class predecessors"); E=$(ln "E: greedy keep flags, fixed point of keep\[q\] = !any(supp\[q\] & keep) ----"); F=$(ln "F: output slot of every rank position")
 DC=$(ln "^// Phase A: decode one cell"); DK=$(ln "^// Direct kernel: one warp per image"); TK=$(ln "decode_nms_tma_kernel(const E"); TE=$(ln "^// Cooperative kernel for big images")
@@ -27,7 +27,13 @@ CD=$(ln "D: suppression words against same-class predecessors"); CE=$(ln "E: gre
 (echo "# loss_gather_kernel<true>, batch 4096 (cfg3) (ncu --set full --clock-control none --import-source on), round 2, commit $REV"
  python profiles/ncu_summarize.py gpurun_out/prof_r2_loss.ncu-rep 4096 | sed -n 1,24p; echo
  python profiles/ncu_lines.py gpurun_out/prof_r2_loss.ncu-rep 4096 20) > profiles/ncu_r2_loss_summary.txt
-(echo "# map_radix_kernel, cfg4: 73,595 records of 5,000 images (ncu --set full --clock-control none --import-source on), round 2, commit $REV; units = records"
+(echo "# map_radix_kernel on its COUNTING path (default), cfg4: 73,595 records of 5,000 images (ncu --set full --clock-control none --import-source on), round 2, commit $REV; units = records"
+ python profiles/ncu_summarize.py gpurun_out/prof_r2_map_count_cfg4.ncu-rep 73595 | sed -n 1,24p; echo
+ python profiles/ncu_lines.py gpurun_out/prof_r2_map_count_cfg4.ncu-rep 73595 24) > profiles/ncu_r2_map_count_cfg4_summary.txt
+(echo "# loss_stream_kernel<true>, batch 16,384 (ncu --set full --clock-control none --import-source on), round 2, commit $REV"
+ python profiles/ncu_summarize.py gpurun_out/prof_r2_loss_stream_b16k.ncu-rep 16384 | sed -n 1,24p; echo
+ python profiles/ncu_lines.py gpurun_out/prof_r2_loss_stream_b16k.ncu-rep 16384 20) > profiles/ncu_r2_loss_stream_b16k_summary.txt
+(echo "# map_radix_kernel with YH_MAP_COUNT=0 (radix passes only), cfg4: 73,595 records of 5,000 images (ncu --set full --clock-control none --import-source on), round 2, commit $REV; units = records"
  python profiles/ncu_summarize.py gpurun_out/prof_r2_map_radix_cfg4.ncu-rep 73595 | sed -n 1,24p; echo
  python profiles/ncu_lines.py gpurun_out/prof_r2_map_radix_cfg4.ncu-rep 73595 24) > profiles/ncu_r2_map_radix_cfg4_summary.txt
 (echo "# map_radix_kernel, 14.7 M records of 1 M images (ncu --set full --clock-control none --import-source on), round 2, commit $REV; units = records"
