@@ -186,7 +186,11 @@ YH_API int yh_map_match(const float *true_rows, int64_t nt, const int64_t *nt_de
 /* Stage 2 (on the records of all shards concatenated in shard order = image order, and the
  * per-class ground-truth counts summed): ONE persistent cooperative kernel - stable radix sort
  * by (class asc, confidence desc), cumulative TP / FP, precision / recall, np.trapz AP per class
- * (out_ap (C), nullable) and the mean over all C classes (out_map (1)).  nrec_dev (nullable):
+ * (out_ap (C), nullable) and the mean over all C classes (out_map (1)).  For small and medium
+ * inputs the kernel takes a sort-free path with bit-identical results (the np.trapz term of a
+ * true positive needs only two ranks, which are counted inside (class, confidence bucket)
+ * groups after one unordered partition); the choice is made on the device from the record and
+ * pair counts (YH_MAP_COUNT=0 in the environment forces the sort).  nrec_dev (nullable):
  * DEVICE int64 record count (<= nrec, which then only bounds the buffers); n_hint: expected
  * record count (sizes the grid only, any value is correct; 0 = nrec).  workspace:
  * yh_workspace_bytes(YH_OP_MAP_REDUCE, nrec, ..) bytes, 256-byte aligned, or NULL.  No host

@@ -56,7 +56,10 @@ def test_decode_nms_random_shapes():
                 _check(yu.decode_nms(h, C, B, it, ct, return_index=True), wh, what + f" ({dt})")
 
 
-def test_loss_random_shapes():
+def test_loss_random_shapes(monkeypatch):
+    """Random grids / boxes / classes / batch sizes through every loss kernel (TMA ring, gather, stream - the stream kernel
+    hands shapes whose tiles do not fit its shared memory to the gather kernel): terms against the C port, gradients
+    bit-identical between the kernels."""
     from yolohot import loss as yl
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(7)
@@ -69,9 +72,21 @@ def test_loss_random_shapes():
             n = max(1, 3_000_000 // (S * S * (C + 5 * B)))
         yt = F.synth_labels(n, S, B, C, seed=trial, lam=float(rng.choice([0.3, 2.5, 20.0])))
         yp = F.synth_loss_pred(yt.shape, seed=trial)
-        terms = yl.yolo_v1_loss_terms(torch.from_numpy(yt).to(dev), torch.from_numpy(yp).to(dev), C, B).cpu().numpy()
         want = cport.loss(yt, yp, C, B)
-        np.testing.assert_allclose(terms, want, rtol=1e-5, atol=1e-6, err_msg=f"trial {trial}: S={S} B={B} C={C} n={n}")
+        td, pd = torch.from_numpy(yt).to(dev), torch.from_numpy(yp).to(dev)
+        grads = []
+        for mode in (None, "0", "1", "2"):
+            if mode is None:
+                monkeypatch.delenv("YH_LOSS_GATHER", raising=False)
+            else:
+                monkeypatch.setenv("YH_LOSS_GATHER", mode)
+            terms, g = yl.yolo_v1_loss_terms(td, pd, C, B, grad=True)
+            np.testing.assert_allclose(terms.cpu().numpy(), want, rtol=1e-5, atol=1e-6,
+                                       err_msg=f"trial {trial}: S={S} B={B} C={C} n={n} kernel={mode}")
+            grads.append(g)
+        monkeypatch.delenv("YH_LOSS_GATHER", raising=False)
+        for g in grads[1:]:
+            assert torch.equal(g, grads[0]), f"trial {trial}: S={S} B={B} C={C} n={n}: gradients differ between the kernels"
 
 
 def test_map_random_rows():
