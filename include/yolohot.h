@@ -154,6 +154,19 @@ YH_API int yh_eval_update(const float *pred_boxes, const int32_t *pred_count,
                    float *pred_rows, int64_t pred_capacity, float *true_rows, int64_t true_capacity,
                    uint64_t *rec, int64_t *cursors, int32_t *gt_per_class, void *stream);
 
+/* ---- evaluator update, fused: MeanAveragePrecision.update_state (utils.py:470-491) in ONE launch.
+ * y_true, y_pred (n, S, S, C+5B) float32, 8-byte aligned: per image one warp runs the fused decode + NMS
+ * of the prediction cells and of the label cells (utils.py:475 / :480, thresholds nms_iou_thr /
+ * nms_conf_thr - the reference hard-codes 0.5 / 0.4), matches the image (match_iou_thr, utils.py:496)
+ * while its kept rows are still in shared memory, and appends rows and records exactly like
+ * yh_eval_update (same buffers, cursors and record layout; the results are bit-identical to
+ * yh_decode_nms x 2 + yh_eval_update).  Grids of more than 64 cells, or class counts whose tables do
+ * not fit shared memory, return YH_ERR_UNSUPPORTED: use the three calls. */
+YH_API int yh_eval_update_state(const float *y_true, const float *y_pred, int64_t n, int S, int B, int C,
+                         float nms_iou_thr, float nms_conf_thr, int64_t img_base, float match_iou_thr,
+                         float *pred_rows, int64_t pred_capacity, float *true_rows, int64_t true_capacity,
+                         uint64_t *rec, int64_t *cursors, int32_t *gt_per_class, void *stream);
+
 /* ---- loss: loss.py:120-215 YoloV1Loss.call (+ its autodiff backward) ------------------
  * y_true, y_pred: (n_cells, C+5B) i.e. the (N,S,S,D) tensors flattened over cells.
  * out_terms: 6 floats [xy, wh, obj, noobj, cls, total] (batch sums, loss.py:172-213).

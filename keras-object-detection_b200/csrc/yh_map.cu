@@ -43,36 +43,6 @@ int keep_pool()
     return YH_OK;
 }
 
-// ---- single-pass chained scan state --------------------------------------------------------------------------
-constexpr int kScanMaxTiles = 1024;
-constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValMask = (1ull << 62) - 1;
-struct ScanWs {                       // all zero at rest: the last CTA of a launch cleans up after the others
-    unsigned ticket, done, pad0, pad1;
-    unsigned long long st[2][kScanMaxTiles];   // [set][tile]: flag << 62 | value;  set 0 = predictions, 1 = ground truth
-};
-
-// exclusive prefix of tile b >= 1 (sum of the totals of the tiles before it), one full warp, 32 tiles per step
-__device__ __forceinline__ long long lookback(volatile unsigned long long *st, int b, int lane)
-{
-    long long prefix = 0;
-    int hi = b - 1;
-    while (true) {
-        const int j = hi - lane;
-        unsigned long long w = kFlagIncl;                       // before tile 0: inclusive prefix 0
-        if (j >= 0) {
-            do { w = st[j]; } while ((w >> 62) == 0);             // tiles with a lower ticket are running or done
-        }
-        const uint32_t incl = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-        const int first = incl ? __ffs(incl) - 1 : 31;            // nearest tile with an inclusive prefix
-        long long v = (lane <= first) ? static_cast<long long>(w & kValMask) : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        prefix += v;
-        if (incl) return prefix;
-        hi -= 32;
-    }
-}
-
 struct EvalArgs {
     const float *boxes[2];            // padded NMS output (n, M, 6): [0] predictions, [1] ground truth (nullable)
     const int32_t *count[2];          // (n)
@@ -176,63 +146,12 @@ __global__ void __launch_bounds__(256) eval_update_kernel(EvalArgs a, ScanWs *ws
             }
         }
         if (!MATCH) continue;
-        const float *pb = a.boxes[0] + img * a.M * 6;
-        const float *tb = a.boxes[1] + img * a.M * 6;
-        const int np_i = cnt[0], nt_i = cnt[1];
-        if (lane < YH_MAX_CELLS / 32) claimed_s[warp][lane] = 0;
-        for (int g = lane; g < nt_i; g += 32) {
-            const uint32_t gc = class_of(tb[g * 6], a.C);
-            if (gc < static_cast<uint32_t>(a.C)) atomicAdd(&hist[gc], 1);            // utils.py:330 rows of the class
-        }
-        __syncwarp();
-        for (int d0 = 0; d0 < np_i; d0 += 32) {
-            const int d = d0 + lane;
-            const bool valid = d < np_i;
-            float conf = 0.0f, dx = 0.0f, dy = 0.0f, dw = 0.0f, dh = 0.0f;
-            uint32_t dc = static_cast<uint32_t>(a.C);
-            if (valid) {
-                const float2 v0 = *reinterpret_cast<const float2 *>(pb + d * 6);
-                const float2 v1 = *reinterpret_cast<const float2 *>(pb + d * 6 + 2);
-                const float2 v2 = *reinterpret_cast<const float2 *>(pb + d * 6 + 4);
-                dc = class_of(v0.x, a.C);
-                conf = v0.y; dx = v1.x; dy = v1.y; dw = v2.x; dh = v2.y;
-            }
-            float best = 0.0f;                                               // utils.py:382 (unwritten slot reads 0)
-            int bj = 0;                                                      // utils.py:383
-            for (int g0 = 0; g0 < nt_i; g0 += 32) {
-                const int g = g0 + lane;
-                uint32_t gc = 0xffffffffu;
-                float gx = 0.0f, gy = 0.0f, gw = 0.0f, gh = 0.0f;
-                if (g < nt_i) {
-                    const float2 v0 = *reinterpret_cast<const float2 *>(tb + g * 6);
-                    const float2 v1 = *reinterpret_cast<const float2 *>(tb + g * 6 + 2);
-                    const float2 v2 = *reinterpret_cast<const float2 *>(tb + g * 6 + 4);
-                    gc = class_of(v0.x, a.C);
-                    gx = v1.x; gy = v1.y; gw = v2.x; gh = v2.y;
-                }
-                const int lim = min(32, nt_i - g0);
-                for (int k = 0; k < lim; ++k) {                              // utils.py:386: ground truths of the image in row order
-                    const uint32_t kc = __shfl_sync(0xffffffffu, gc, k);
-                    const float kx = __shfl_sync(0xffffffffu, gx, k), ky = __shfl_sync(0xffffffffu, gy, k);
-                    const float kw = __shfl_sync(0xffffffffu, gw, k), kh = __shfl_sync(0xffffffffu, gh, k);
-                    if (kc == dc && dc < static_cast<uint32_t>(a.C)) {
-                        const float v = iou_ref(dx, dy, dw, dh, kx, ky, kw, kh);         // utils.py:387 (det, gt)
-                        if (v > best) { best = v; bj = g0 + k; }                        // utils.py:389
-                    }
-                }
-            }
-            const bool hit = valid && best > a.iou_thr;                                // utils.py:395
-            const bool taken = hit && ((claimed_s[warp][bj >> 5] >> (bj & 31)) & 1u);  // claimed by an earlier chunk
-            const uint32_t peers = __match_any_sync(0xffffffffu, (hit && !taken) ? static_cast<uint32_t>(bj) : 0x10000u + lane);
-            const bool tp = hit && !taken && lane == __ffs(peers) - 1;                 // utils.py:408-418: first in order claims
-            __syncwarp();
-            if (tp) atomicOr(&claimed_s[warp][bj >> 5], 1u << (bj & 31));
-            __syncwarp();
-            if (valid) {
-                const long long r = row0[0] + d;
-                if (r < a.cap[0]) a.rec[r] = make_rec(dc, conf, tp ? 1u : 0u);
-            }
-        }
+        const long long r0 = row0[0];
+        match_image(a.boxes[0] + img * a.M * 6, a.boxes[1] + img * a.M * 6, cnt[0], cnt[1], a.C, a.iou_thr, claimed_s[warp], hist, lane,
+                    [&](int d, unsigned long long rec) {
+                        const long long r = r0 + d;
+                        if (r < a.cap[0]) a.rec[r] = rec;
+                    });
         __syncwarp();
     }
     __syncthreads();
@@ -256,7 +175,7 @@ __global__ void __launch_bounds__(256) eval_update_kernel(EvalArgs a, ScanWs *ws
 static std::mutex g_scan_mu;
 static std::map<std::pair<int, cudaStream_t>, ScanWs *> g_scan_ws;
 
-static int scan_ws_for(cudaStream_t st, ScanWs **out)
+int scan_ws_for(cudaStream_t st, ScanWs **out)
 {
     int dev = 0;
     YH_CUDA(cudaGetDevice(&dev));

@@ -23,7 +23,7 @@ _lib = None
 SYMBOLS = (
     "yh_version", "yh_last_error", "yh_device_info", "yh_launch_count",
     "yh_iou", "yh_decode", "yh_nms", "yh_decode_nms", "yh_decode_nms_ex", "yh_decode_nms_host", "yh_decode_nms_host_typed", "yh_decode_nms_host_rows", "yh_host_alloc", "yh_host_free", "yh_filter_rows", "yh_rows_append",
-    "yh_loss", "yh_eval_update", "yh_map_match", "yh_map_reduce",
+    "yh_loss", "yh_eval_update", "yh_eval_update_state", "yh_map_match", "yh_map_reduce",
     "yh_encode_labels", "yh_head_to_f32", "yh_decode_nms_typed", "yh_pixel_boxes",
     "yh_comm_init_all", "yh_comm_destroy", "yh_map_allgather", "yh_comm_p2p", "yh_comm_barrier",
     "yh_map_exchange_bytes", "yh_map_exchange", "yh_map_reduce_exchanged",
@@ -66,6 +66,7 @@ def lib():
     L.yh_rows_append.argtypes = [vp, vp, i64, i, i64, vp, i64, vp, vp]
     L.yh_loss.argtypes = [vp, vp, i64, i, i, f, f, vp, vp, vp]
     L.yh_eval_update.argtypes = [vp, vp, vp, vp, i64, i, i64, i, f, vp, i64, vp, i64, vp, vp, vp, vp]
+    L.yh_eval_update_state.argtypes = [vp, vp, i64, i, i, i, f, f, i64, f, vp, i64, vp, i64, vp, vp, vp, vp]
     L.yh_map_match.argtypes = [vp, i64, vp, vp, i64, vp, i, f, i, vp, vp, vp, C.c_size_t, vp]
     L.yh_map_reduce.argtypes = [vp, i64, vp, i64, vp, i, vp, vp, vp, C.c_size_t, vp]
     L.yh_map_exchange_bytes.argtypes = [i, i, i64]

@@ -17,6 +17,7 @@ the producer's kind.  There is no CPU implementation behind any of these names."
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -349,8 +350,9 @@ def mean_average_precision_2(true_bboxes, pred_bboxes, iou_threshold=0.5, num_cl
 class MeanAveragePrecision:
     """utils.py:459-496.  reset_states() / update_state(y_true, y_pred) / result().
 
-    update_state is three launches and no host synchronisation: fused decode + NMS of the predictions, of the
-    ground truth (utils.py:475 / :480), and ONE accumulation kernel (yh_eval_update) that appends both row sets to
+    update_state is ONE launch and no host synchronisation (yh_eval_update_state; grids of more than 64 cells: three -
+    fused decode + NMS of the predictions, of the ground truth (utils.py:475 / :480), and the accumulation kernel
+    yh_eval_update): per image, decode + NMS of both tensors, then both row sets are appended to
     append-only device buffers (instead of the reference's O(total^2) re-concatenation, utils.py:484-489) and
     matches every image on the spot, leaving one packed (class, confidence, TP) record per detection.  result() is
     one more launch (yh_map_reduce: sort + cumulative TP/FP + AP + mean) and returns a 0-d device tensor.
@@ -434,6 +436,19 @@ class MeanAveragePrecision:
         if self.img_idx == 0:                       # utils.py:484-486: first image overwrites
             st["state"].zero_()
             st["bound"] = 0
+        if (self._nms_true and M <= 64 and yt.data_ptr() % 8 == 0 and yp.data_ptr() % 8 == 0
+                and os.environ.get("YH_EVAL_FUSED", "1") != "0"):
+            # one launch: decode + NMS of both tensors, matching and append per image while its rows are in shared memory
+            with on_device(dev):
+                rc = _lib.lib().yh_eval_update_state(yt.data_ptr(), yp.data_ptr(), n, S, self._num_boxes, self._num_classes, 0.5, 0.4,
+                                                     int(self.img_idx), self._IOU_THR, st["pred"].data_ptr(), st["cap"],
+                                                     st["true"].data_ptr(), st["cap"], st["rec"].data_ptr(), st["cursors"].data_ptr(),
+                                                     st["gt"].data_ptr(), stream_ptr(dev))
+            if rc != _lib.YH_ERR_UNSUPPORTED:          # (class tables that do not fit shared memory: the three launches below)
+                _lib.check(rc, "update_state")
+                st["bound"] += n * M
+                self.img_idx += n                        # utils.py:491
+                return
         key = (n, M)
         bufs = self._cache.get(key)
         if bufs is None:                            # padded NMS outputs of one batch, reused by the next one

@@ -126,6 +126,33 @@ def test_counting_path_equals_radix_path(dev, n, C, quant, skew, monkeypatch):
         assert torch.equal(m1.view(torch.int32), m0.view(torch.int32)), env
 
 
+@pytest.mark.parametrize("S,B,C,n1,n2", [(7, 2, 20, 300, 77), (5, 1, 3, 64, 9), (8, 3, 80, 130, 1), (3, 2, 20, 1000, 555)])
+def test_fused_update_state_equals_three_launches(dev, monkeypatch, S, B, C, n1, n2):
+    """update_state as ONE kernel (yh_eval_update_state: decode + NMS of both tensors, matching, append) against the
+    three-launch path (yh_decode_nms x 2 + yh_eval_update) over two batches: row buffers, records, cursors, per-class
+    ground-truth counts and the mAP, bit for bit - specialised VOC shape, generic shapes, a 64-cell grid."""
+    from yolohot import utils as yu
+    out = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("YH_EVAL_FUSED", fused)
+        ev = yu.MeanAveragePrecision(C, B)
+        for k, (n, seed) in enumerate(((n1, 3), (n2, 4))):
+            yt = F.synth_labels(n, S, B, C, seed=seed, lam=2.5)
+            yp = F.synth_map_pred(yt, B, C, seed=seed)
+            ev.update_state(torch.from_numpy(yt).to(dev), torch.from_numpy(yp).to(dev))
+        m = ev.result()
+        torch.cuda.synchronize()
+        st = ev._st
+        npred, ntrue = int(st["cursors"][0]), int(st["cursors"][1])
+        out[fused] = (npred, ntrue, st["pred"][:npred].clone(), st["true"][:ntrue].clone(), st["rec"][:npred].clone(),
+                      st["gt"].clone(), m.clone(), ev.last_ap.clone())
+    monkeypatch.delenv("YH_EVAL_FUSED")
+    a, b = out["0"], out["1"]
+    assert a[0] == b[0] and a[1] == b[1] and a[0] > 0 and a[1] > 0
+    for x, y in zip(a[2:], b[2:]):
+        assert torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x, y.view(torch.int32) if y.dtype == torch.float32 else y)
+
+
 def test_rows_append_chained_scan(dev):
     """yh_rows_append / yh_eval_update row buffers against a NumPy compaction, from one tile to a thousand."""
     from yolohot import _lib
