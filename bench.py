@@ -696,7 +696,7 @@ def cfg4_map(ctx):
            "ms_update_plus_result": _max_over_ranks(ctx, wall_ms), "gpu_ms_update_plus_result": _max_over_ranks(ctx, gpu_ms),
            "ms_update_plus_result_host_read": _max_over_ranks(ctx, statistics.median(sync_ms)),
            "kernel_launches_per_pass": launches, "host_syncs_per_pass": 0,
-           "path": "decode+NMS x2 -> yh_eval_update (append + match) -> " +
+           "path": "yh_eval_update_state (decode+NMS of y_pred and y_true, match, append: one kernel) -> " +
                    ("yh_map_exchange (peer stores over NVLink) -> yh_map_reduce_exchanged" if world > 1 else "yh_map_reduce")}
     if world > 1:
         ok = torch.tensor([1 if mval == m_single else 0], device=dev, dtype=torch.int32)

@@ -29,7 +29,9 @@ ncu --set full --clock-control none --import-source on -k regex:map_radix_kernel
     -o gpurun_out/prof_r2_map_count_cfg4 -f python profiles/prof_map.py cfg4 > gpurun_out/ncu_map_r2.log 2>&1
 YH_MAP_COUNT=0 ncu --set full --clock-control none --import-source on -k regex:map_radix_kernel --launch-skip 4 --launch-count 1 \
     -o gpurun_out/prof_r2_map_radix_cfg4 -f python profiles/prof_map.py cfg4 >> gpurun_out/ncu_map_r2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:eval_update_kernel --launch-skip 4 --launch-count 1 \
+ncu --set full --clock-control none --import-source on -k regex:eval_state_kernel --launch-skip 4 --launch-count 1 \
+    -o gpurun_out/prof_r2_eval_state_cfg4 -f python profiles/prof_map.py cfg4 >> gpurun_out/ncu_map_r2.log 2>&1
+YH_EVAL_FUSED=0 ncu --set full --clock-control none --import-source on -k regex:eval_update_kernel --launch-skip 4 --launch-count 1 \
     -o gpurun_out/prof_r2_eval_update_cfg4 -f python profiles/prof_map.py cfg4 >> gpurun_out/ncu_map_r2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:map_radix_kernel --launch-skip 2 --launch-count 1 \
     -o gpurun_out/prof_r2_map_radix_big -f python profiles/prof_map.py big >> gpurun_out/ncu_map_r2.log 2>&1

@@ -10,7 +10,7 @@ cp gpurun_out/launches_r2_map.csv profiles/launches_r2_map_cfg4.csv
 cp gpurun_out/bench_r2_final.json profiles/bench_r2_final.json
 cp gpurun_out/bench_r2_ref.json profiles/bench_r2_reference_arm.json
 python profiles/launch_summary.py gpurun_out/launches_r2_final.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 2 --warmup 1 (YH_BENCH_SUSTAINED=20)" > profiles/launches_r2_final_summary.txt
-python profiles/launch_summary.py gpurun_out/launches_r2_map.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 200 python profiles/prof_map.py cfg4 (13 evaluator passes of 5,000 images: 4 launches each + 1 torch fill; reduce on its counting path)" > profiles/launches_r2_map_cfg4_summary.txt
+python profiles/launch_summary.py gpurun_out/launches_r2_map.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 200 python profiles/prof_map.py cfg4 (13 evaluator passes of 5,000 images: 2 launches each + 1 torch fill; fused update_state, reduce on its counting path)" > profiles/launches_r2_map_cfg4_summary.txt
 A=$(ln "A': compaction of the survivors"); B=$(ln "B: stable descending rank (utils.py:98): r ="); T=$(ln "a duplicate rank <=> equal confidences"); K=$(ln "class key: the class id itself")
 C=$(ln "C: same-class masks.  Slot t"); D=$(ln "D: suppression bits against same-class predecessors"); E=$(ln "E: greedy keep flags, fixed point of keep\[q\] = !any(supp\[q\] & keep) ----"); F=$(ln "F: output slot of every rank position")
 DC=$(ln "^// Phase A: decode one cell"); DK=$(ln "^// Direct kernel: one warp per image"); TK=$(ln "decode_nms_tma_kernel(const E"); TE=$(ln "^// Cooperative kernel for big images")
@@ -39,7 +39,10 @@ CD=$(ln "D: suppression words against same-class predecessors"); CE=$(ln "E: gre
 (echo "# map_radix_kernel, 14.7 M records of 1 M images (ncu --set full --clock-control none --import-source on), round 2, commit $REV; units = records"
  python profiles/ncu_summarize.py gpurun_out/prof_r2_map_radix_big.ncu-rep 14668340 | sed -n 1,24p; echo
  python profiles/ncu_lines.py gpurun_out/prof_r2_map_radix_big.ncu-rep 14668340 24) > profiles/ncu_r2_map_radix_1M_images_summary.txt
-(echo "# eval_update_kernel<true>, cfg4: one batch of 5,000 images (ncu --set full --clock-control none --import-source on), round 2, commit $REV; units = images"
+(echo "# eval_state_kernel<2,20,2> (update_state in one launch), cfg4: one batch of 5,000 images (ncu --set full --clock-control none --import-source on), round 2, commit $REV; units = images"
+ python profiles/ncu_summarize.py gpurun_out/prof_r2_eval_state_cfg4.ncu-rep 5000 | sed -n 1,24p; echo
+ python profiles/ncu_lines.py gpurun_out/prof_r2_eval_state_cfg4.ncu-rep 5000 20) > profiles/ncu_r2_eval_state_cfg4_summary.txt
+(echo "# eval_update_kernel<true> (three-launch path, YH_EVAL_FUSED=0), cfg4: one batch of 5,000 images (ncu --set full --clock-control none --import-source on), round 2, commit $REV; units = images"
  python profiles/ncu_summarize.py gpurun_out/prof_r2_eval_update_cfg4.ncu-rep 5000 | sed -n 1,24p; echo
  python profiles/ncu_lines.py gpurun_out/prof_r2_eval_update_cfg4.ncu-rep 5000 20) > profiles/ncu_r2_eval_update_cfg4_summary.txt
 python - <<PY
