@@ -29,3 +29,5 @@ hist yh_map.o 'map_match_kernel' map_match_kernel "matching on arbitrary rows"
 hist yh_map_reduce.o 'map_radix_kernel' map_radix_kernel "mAP reduce: persistent cooperative radix sort + AP"
 hist yh_comm.o 'map_exchange_kernel' map_exchange_kernel "mAP exchange: peer stores + release flags"
 hist yh_adapters.o 'encode_labels_kernel' encode_labels_kernel "label-grid encoder (TMA store)"
+hist yh_loss.o 'loss_stream_kernelILb1E' loss_stream_kernel "loss forward+backward, stream variant: TMA in (UBLKCP.S.G), gradient tile composed in shared memory, TMA out (UBLKCP.G.S)"
+hist yh_eval_fused.o 'eval_state_kernelILi2ELi20ELi2E' eval_state_kernel "update_state in one launch: decode + NMS of both tensors, matching, chained-scan append"
