@@ -418,6 +418,9 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const float *__restr
 #ifndef YH_GATHER_CPT
 #define YH_GATHER_CPT 2
 #endif
+#ifndef YH_GATHER_QUAD
+#define YH_GATHER_QUAD 1
+#endif
 constexpr int kGatherThreads = YH_GATHER_THREADS;
 constexpr int kGatherCPT = YH_GATHER_CPT;                       // cells per thread: fewer, fatter threads keep a cfg3-sized batch in ONE wave
 constexpr int kGatherTile = kGatherThreads * kGatherCPT;
@@ -444,6 +447,12 @@ __global__ void __launch_bounds__(kGatherThreads, 3) loss_gather_kernel(const fl
     const int64_t n_tiles = (cfg.n_cells + kGatherTile - 1) / kGatherTile;
     const bool gvec_ok = kGrad && (reinterpret_cast<uintptr_t>(grad) % 16 == 0) && ((static_cast<int64_t>(kGatherTile) * D) % 4 == 0);
     const bool pair_ok = (((C | D) & 1) == 0) && (reinterpret_cast<uintptr_t>(yt) % 8 == 0);   // y_true[C..C+3] as two aligned pairs
+    // Thread = two CONSECUTIVE cells (an even / odd pair starts on a 16-byte boundary when C % 4 == 0 and D is even): the five
+    // deciding values of y_true come as one 16-byte and one 8-byte load per cell - LDG.128 [C..C+3] + LDG.64 [C+4..C+5] for the
+    // even cell, LDG.64 [C..C+1] + LDG.128 [C+2..C+5] for the odd one - three requests per cell with y_pred[C] instead of four.
+    // The gathers are bound by the SM's miss tracking (timeline in profiles/README.md), so requests are what counts.
+    static_assert(kGatherCPT == 2, "the consecutive-pair mapping below is written for two cells per thread");
+    const bool quad_ok = (C % 4 == 0) && (D % 2 == 0) && (D >= C + 6) /* [C+5] is read: B >= 2 */ && (reinterpret_cast<uintptr_t>(yt) % 16 == 0) && YH_GATHER_QUAD;
     double sxy = 0, swh = 0, sob = 0, snb = 0, scl = 0;
     if (kGrad && gvec_ok) {
         float4 *z4 = reinterpret_cast<float4 *>(zeros);
@@ -458,11 +467,24 @@ __global__ void __launch_bounds__(kGatherThreads, 3) loss_gather_kernel(const fl
         bool in[kGatherCPT];
 #pragma unroll
         for (int j = 0; j < kGatherCPT; ++j) {                               // every load of the thread in flight together
-            const int cell = j * kGatherThreads + threadIdx.x;
+            const int cell = quad_ok ? 2 * static_cast<int>(threadIdx.x) + j : j * kGatherThreads + static_cast<int>(threadIdx.x);
             in[j] = cell < cells;
             obj[j] = b1[j] = b2[j] = b3[j] = b4[j] = c0[j] = 0.f;
             if (in[j]) {
                 const float *t = yt + (cell0 + cell) * D + C;
+                if (quad_ok) {                                               // (cell0 is even: the parity of the cell is j)
+                    if (j == 0) {
+                        const float4 u = __ldg(reinterpret_cast<const float4 *>(t));
+                        const float2 v = __ldg(reinterpret_cast<const float2 *>(t + 4));
+                        obj[j] = u.x; b1[j] = u.y; b2[j] = u.z; b3[j] = u.w; b4[j] = v.x;
+                    } else {
+                        const float2 u = __ldg(reinterpret_cast<const float2 *>(t));
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(t + 2));
+                        obj[j] = u.x; b1[j] = u.y; b2[j] = v.x; b3[j] = v.y; b4[j] = v.z;
+                    }
+                    c0[j] = __ldg(yp + (cell0 + cell) * D + C);
+                    continue;
+                }
                 if (pair_ok) {
                     const float2 u = __ldg(reinterpret_cast<const float2 *>(t));
                     const float2 v = __ldg(reinterpret_cast<const float2 *>(t + 2));
@@ -524,7 +546,7 @@ __global__ void __launch_bounds__(kGatherThreads, 3) loss_gather_kernel(const fl
                 base += (w < warp) ? k : 0;
                 n_heavy += k;
             }
-            const int cell = j * kGatherThreads + threadIdx.x;
+            const int cell = quad_ok ? 2 * static_cast<int>(threadIdx.x) + j : j * kGatherThreads + static_cast<int>(threadIdx.x);
             if (hv[j]) heavy[base + __popc(bal[j] & ((1u << lane) - 1u))] = cell;
             if (kGrad && in[j] && !hv[j]) grad[(cell0 + cell) * D + C] = g_light[j];
         }
