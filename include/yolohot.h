@@ -161,7 +161,9 @@ YH_API int yh_eval_update(const float *pred_boxes, const int32_t *pred_count,
  * while its kept rows are still in shared memory, and appends rows and records exactly like
  * yh_eval_update (same buffers, cursors and record layout; the results are bit-identical to
  * yh_decode_nms x 2 + yh_eval_update).  Grids of more than 64 cells, or class counts whose tables do
- * not fit shared memory, return YH_ERR_UNSUPPORTED: use the three calls. */
+ * not fit shared memory, return YH_ERR_UNSUPPORTED: use the three calls.  One launch wins where three
+ * are latency - up to about 8,000 VOC-sized images per call on a B200 (33 vs 45 us at 5,000); beyond
+ * that the TMA tile kernels behind yh_decode_nms stream the cells faster (85 vs 132 us at 20,000). */
 YH_API int yh_eval_update_state(const float *y_true, const float *y_pred, int64_t n, int S, int B, int C,
                          float nms_iou_thr, float nms_conf_thr, int64_t img_base, float match_iou_thr,
                          float *pred_rows, int64_t pred_capacity, float *true_rows, int64_t true_capacity,

@@ -436,9 +436,13 @@ class MeanAveragePrecision:
         if self.img_idx == 0:                       # utils.py:484-486: first image overwrites
             st["state"].zero_()
             st["bound"] = 0
+        fused_env = os.environ.get("YH_EVAL_FUSED", "")           # "0" / "1" force a path; default: by batch size
         if (self._nms_true and M <= 64 and yt.data_ptr() % 8 == 0 and yp.data_ptr() % 8 == 0
-                and os.environ.get("YH_EVAL_FUSED", "1") != "0"):
-            # one launch: decode + NMS of both tensors, matching and append per image while its rows are in shared memory
+                and (fused_env == "1" or (fused_env != "0" and n * M <= 400_000))):
+            # one launch: decode + NMS of both tensors, matching and append per image while its rows are in shared memory.
+            # Batches of up to ~8,000 VOC images, where three launches are latency (B200, us per update_state at 2,000 /
+            # 5,000 / 10,000 / 20,000 images: 23 / 33 / 65 / 132 fused, 34 / 45 / 59 / 85 as three launches); beyond that the
+            # TMA tile kernels of the three-launch path stream the cells faster than one warp per image can fetch them
             with on_device(dev):
                 rc = _lib.lib().yh_eval_update_state(yt.data_ptr(), yp.data_ptr(), n, S, self._num_boxes, self._num_classes, 0.5, 0.4,
                                                      int(self.img_idx), self._IOU_THR, st["pred"].data_ptr(), st["cap"],
