@@ -612,7 +612,14 @@ __global__ void __launch_bounds__(kGatherThreads, 3) loss_gather_kernel(const fl
 // Bit-identical gradients and per-cell terms to the other two kernels (same device functions).
 // ------------------------------------------------------------------------------------------
 constexpr int kStreamThreads = 64;                              // = cells per tile
-constexpr int kStreamStages = 2;
+#ifndef YH_STREAM_STAGES
+#define YH_STREAM_STAGES 2
+#endif
+constexpr int kStreamStages = YH_STREAM_STAGES;
+#ifndef YH_STREAM_GBUFS
+#define YH_STREAM_GBUFS 2
+#endif
+constexpr int kStreamGbufs = YH_STREAM_GBUFS;              // gradient tiles in shared memory (2: a store may still be read while the next is composed)
 
 template <bool kGrad>
 __global__ void __launch_bounds__(kStreamThreads) loss_stream_kernel(const float *__restrict__ yt, const float *__restrict__ yp,
@@ -629,7 +636,7 @@ __global__ void __launch_bounds__(kStreamThreads) loss_stream_kernel(const float
     const uint32_t tile_bytes = static_cast<uint32_t>(tile_fl) * 4u;                 // 256 * D: a multiple of 16
     float *ring = reinterpret_cast<float *>(smem);                                    // [stage][y_true tile | y_pred tile]
     float *gbuf = ring + static_cast<size_t>(kStreamStages) * 2 * tile_fl;            // [2][tile] gradient tiles (double buffered)
-    uint64_t *full = reinterpret_cast<uint64_t *>(gbuf + 2 * static_cast<size_t>(tile_fl));
+    uint64_t *full = reinterpret_cast<uint64_t *>(gbuf + kStreamGbufs * static_cast<size_t>(tile_fl));
     int *heavy = reinterpret_cast<int *>(full + kStreamStages);                       // [TT]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (cfg.n_cells + TT - 1) / TT;
@@ -653,10 +660,12 @@ __global__ void __launch_bounds__(kStreamThreads) loss_stream_kernel(const float
         bulk_g2s(ring + static_cast<size_t>(s) * 2 * tile_fl, yt + off, tile_bytes, full + s, pol);
         bulk_g2s(ring + static_cast<size_t>(s) * 2 * tile_fl + tile_fl, yp + off, tile_bytes, full + s, pol);
     };
-    if (threadIdx.x == 0 && my_tiles > 0 && in_ok && cells_of(0) == TT) issue(0);
+    if (threadIdx.x == 0)
+        for (int64_t it = 0; it < my_tiles && it < kStreamStages - 1; ++it)
+            if (in_ok && cells_of(it) == TT) issue(it);
     if (kGrad) {                                                                      // both gradient tiles start as zeros
         float4 *g4 = reinterpret_cast<float4 *>(gbuf);
-        for (int i = threadIdx.x; i < (2 * tile_fl) >> 2; i += TT) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = threadIdx.x; i < (kStreamGbufs * tile_fl) >> 2; i += TT) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     double sxy = 0, swh = 0, sob = 0, snb = 0, scl = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
@@ -666,13 +675,16 @@ __global__ void __launch_bounds__(kStreamThreads) loss_stream_kernel(const float
         const int cells = cells_of(it);
         float *st = ring + static_cast<size_t>(s) * 2 * tile_fl;
         float *sp = st + tile_fl;
-        float *gb = gbuf + static_cast<size_t>(it & 1) * tile_fl;
+        float *gb = gbuf + static_cast<size_t>(it % kStreamGbufs) * tile_fl;
         const bool bulk_in = in_ok && cells == TT;
-        // the other stage was read by tile it-1, which every thread left at the barrier that ends an iteration
-        if (threadIdx.x == 0 && it + 1 < my_tiles && in_ok && cells_of(it + 1) == TT) issue(it + 1);
-        if (kGrad && it >= 2) {
-            // this gradient buffer left with tile it-2: once the TMA engine has read it, make it zeros again
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // the stage of tile it + stages - 1 was read by tile it-1, which every thread left at the barrier that ends an iteration
+        if (threadIdx.x == 0 && it + kStreamStages - 1 < my_tiles && in_ok && cells_of(it + kStreamStages - 1) == TT) issue(it + kStreamStages - 1);
+        if (kGrad && it >= kStreamGbufs) {
+            // this gradient buffer left with tile it - kStreamGbufs: once the TMA engine has read it, make it zeros again
+            if (threadIdx.x == 0) {
+                if (kStreamGbufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
             __syncthreads();
             float4 *g4 = reinterpret_cast<float4 *>(gb);
             for (int i = threadIdx.x; i < tile_fl >> 2; i += TT) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -813,7 +825,7 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
     // forces one of them
     const char *gv = getenv("YH_LOSS_GATHER");                     // read per call: the tests switch it
     const int env_gather = (gv && *gv) ? atoi(gv) : -1;            // 0 = ring, 1 = gather, 2 = stream
-    const size_t smem_stream = static_cast<size_t>(kStreamStages * 2 + 2) * kStreamThreads * cfg.D * 4 + kStreamStages * 8 + kStreamThreads * 4 + 64;
+    const size_t smem_stream = static_cast<size_t>(kStreamStages * 2 + kStreamGbufs) * kStreamThreads * cfg.D * 4 + kStreamStages * 8 + kStreamThreads * 4 + 64;
     // measured (B200, fwd+bwd us at batch 1,024 / 4,096 / 16,384 / 65,536): ring 11.3 / 20.5 / 57.4 / 196, gather 10.6 / 19.7 /
     // 57.7 / 188, stream 11.4 / 20.2 / 52.2 / 179 (6.45 TB/s); forward only: gather 8.2 / 14.3 / 38.7 / 119 beats both
     int which = env_gather >= 0 ? env_gather : (n_cells < (1 << 15) ? 0 : (out_grad && n_cells >= 393216) ? 2 : 1);
@@ -840,8 +852,17 @@ extern "C" int yh_loss(const float *y_true, const float *y_pred, int64_t n_cells
         g.smem = smem;
         g.per_sm = per_sm < 1 ? 1 : per_sm;
     }
-    const int grid = static_cast<int>(
+    int grid = static_cast<int>(
         std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * ((gather || stream_k) ? g.per_sm : std::min(g.per_sm, std::max(1, env_ctas))))));
+    if (stream_k) {
+        // same number of tiles for every CTA (the CTAs walk their tiles in lock step: a last round that only some of them
+        // take leaves the memory system half idle for a whole tile time)
+        static const int env_bal = [] { const char *v = getenv("YH_STREAM_BALANCE"); return (v && *v) ? atoi(v) : 1; }();
+        if (env_bal) {
+            const int64_t rounds = (n_tiles + grid - 1) / grid;
+            grid = static_cast<int>((n_tiles + rounds - 1) / rounds);
+        }
+    }
     // every stream gets its own partials / ticket (launches of one stream are ordered anyway, so nothing has to be
     // recorded or waited for between them); only past kLossStreams streams per device is one block shared through an event
     LossScratch *scp = nullptr;
