@@ -532,12 +532,22 @@ __global__ void __launch_bounds__(RS_T, 2) map_radix_kernel(const __grid_constan
         // ---- histogram of this CTA's range
         if (tid < RS_BINS) sm.hist[tid] = 0;
         __syncthreads();
-        for (long long i0 = lo; i0 < hi; i0 += RS_T) {
-            const long long i = i0 + tid;
-            const bool valid = i < hi;
-            const uint32_t d = valid ? static_cast<uint32_t>(load_in(a, sm, src, i) >> shift) & 0xffu : 256u + lane;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            if (valid && lane == __ffs(peers) - 1) atomicAdd(&sm.hist[d], __popc(peers));
+        for (long long i0 = lo; i0 < hi; i0 += RS_T * RS_IPT) {
+            unsigned long long kk[RS_IPT];
+#pragma unroll
+            for (int j = 0; j < RS_IPT; ++j) {                   // all loads of the thread in flight together (one load per
+                const long long i = i0 + j * RS_T + tid;         // iteration left this phase at 1.2 TB/s: 15 % of the samples)
+                kk[j] = i < hi ? load_in(a, sm, src, i) : 0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < RS_IPT; ++j) {
+                if (i0 + j * RS_T + (tid & ~31) < hi) {          // warp-uniform
+                    const bool valid = i0 + j * RS_T + tid < hi;
+                    const uint32_t d = valid ? static_cast<uint32_t>(kk[j] >> shift) & 0xffu : 256u + lane;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                    if (valid && lane == __ffs(peers) - 1) atomicAdd(&sm.hist[d], __popc(peers));
+                }
+            }
         }
         __syncthreads();
         if (tid < RS_BINS) a.hist[static_cast<size_t>(cta) * RS_BINS + tid] = sm.hist[tid];
@@ -653,16 +663,24 @@ __global__ void __launch_bounds__(RS_T, 2) map_radix_kernel(const __grid_constan
             a.class_start[c] = l;
         }
     }
-    for (long long i0 = lo; i0 < hi; i0 += RS_T) {
-        const long long i = i0 + tid;
-        const bool valid = i < hi;
-        const unsigned long long key = valid ? src[i] : 0ull;
-        const bool tp = valid && (key & 1ull);
-        const uint32_t c = tp ? static_cast<uint32_t>(key >> kRecClassShift) : 0x10000u + lane;
-        const uint32_t peers = __match_any_sync(0xffffffffu, c);
-        if (tp && lane == __ffs(peers) - 1) {
-            atomicAdd(&tp_s[c], __popc(peers));
-            atomicAdd(&sm.cta_tp, __popc(peers));
+    for (long long i0 = lo; i0 < hi; i0 += RS_T * RS_IPT) {
+        unsigned long long kk[RS_IPT];
+#pragma unroll
+        for (int j = 0; j < RS_IPT; ++j) {                       // all loads of the thread in flight together
+            const long long i = i0 + j * RS_T + tid;
+            kk[j] = i < hi ? src[i] : 0ull;                      // (an absent record is no true positive)
+        }
+#pragma unroll
+        for (int j = 0; j < RS_IPT; ++j) {
+            if (i0 + j * RS_T + (tid & ~31) < hi) {              // warp-uniform
+                const bool tp = kk[j] & 1ull;
+                const uint32_t c = tp ? static_cast<uint32_t>(kk[j] >> kRecClassShift) : 0x10000u + lane;
+                const uint32_t peers = __match_any_sync(0xffffffffu, c);
+                if (tp && lane == __ffs(peers) - 1) {
+                    atomicAdd(&tp_s[c], __popc(peers));
+                    atomicAdd(&sm.cta_tp, __popc(peers));
+                }
+            }
         }
     }
     __syncthreads();
@@ -687,10 +705,20 @@ __global__ void __launch_bounds__(RS_T, 2) map_radix_kernel(const __grid_constan
     for (int c = 0; c < cta; ++c) cta_base += a.cta_tp[c];
     __syncthreads();
     uint32_t running = cta_base;
-    for (long long i0 = lo; i0 < hi; i0 += RS_T) {
+    for (long long i00 = lo; i00 < hi; i00 += 4 * RS_T) {
+      unsigned long long kq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {                              // four iterations' loads in flight together
+          const long long i = i00 + q * RS_T + tid;
+          kq[q] = i < hi ? src[i] : 0ull;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long i0 = i00 + q * RS_T;
+        if (i0 >= hi) break;                                     // CTA-uniform
         const long long i = i0 + tid;
         const bool valid = i < hi;
-        const unsigned long long key = valid ? src[i] : 0ull;
+        const unsigned long long key = kq[q];
         const bool tp = valid && (key & 1ull);
         const uint32_t ball = __ballot_sync(0xffffffffu, tp);
         if (lane == 0) sm.wsum[warp] = __popc(ball);
@@ -730,6 +758,7 @@ __global__ void __launch_bounds__(RS_T, 2) map_radix_kernel(const __grid_constan
         }
         running += blk;
         __syncthreads();
+      }
     }
     __syncthreads();
     for (int c = tid; c < C; c += RS_T)
