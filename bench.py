@@ -698,6 +698,32 @@ def cfg4_map(ctx):
            "kernel_launches_per_pass": launches, "host_syncs_per_pass": 0,
            "path": "yh_eval_update_state (decode+NMS of y_pred and y_true, match, append: one kernel) -> " +
                    ("yh_map_exchange (peer stores over NVLink) -> yh_map_reduce_exchanged" if world > 1 else "yh_map_reduce")}
+    if world == 1:
+        # the two stages on their own (back to back, CUDA events): update_state = one kernel, result() = one kernel on its
+        # counting path - and, for comparison, on its radix-sort passes (YH_MAP_COUNT=0 is read per call)
+        def timed(fn, reps=30):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                fn()
+            a1.record()
+            torch.cuda.synchronize(dev)
+            return a0.elapsed_time(a1) / reps * 1e3
+
+        def upd():
+            ev.reset_states()
+            ev.update_state(a, b_)
+        out["us_update_state_alone"] = timed(upd)
+        out["us_result_alone"] = timed(ev.result)
+        os.environ["YH_MAP_COUNT"] = "0"
+        try:
+            out["us_result_alone_radix_passes_only"] = timed(ev.result)
+            out["mAP_radix_passes_only"] = float(ev.result())
+        finally:
+            del os.environ["YH_MAP_COUNT"]
     if world > 1:
         ok = torch.tensor([1 if mval == m_single else 0], device=dev, dtype=torch.int32)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
