@@ -62,8 +62,8 @@ def test_loss_random_shapes(monkeypatch):
     bit-identical between the kernels."""
     from yolohot import loss as yl
     dev = torch.device("cuda:0")
-    rng = np.random.default_rng(7)
-    for trial in range(40):
+    rng = np.random.default_rng(int(os.environ.get("YH_FUZZ_SEED", 7)))
+    for trial in range(int(os.environ.get("YH_FUZZ_TRIALS_LOSS", 40))):
         S = int(rng.integers(1, 15))
         B = int(rng.integers(1, 4))
         C = int(rng.choice([1, 3, 20, 80]))
@@ -94,8 +94,8 @@ def test_map_random_rows():
     classes without ground truth or without detections, images without ground truth) against the C port."""
     from yolohot import utils as yu
     dev = torch.device("cuda:0")
-    rng = np.random.default_rng(99)
-    for trial in range(40):
+    rng = np.random.default_rng(int(os.environ.get("YH_FUZZ_SEED", 99)))
+    for trial in range(int(os.environ.get("YH_FUZZ_TRIALS_MAP", 40))):
         C = int(rng.choice([1, 3, 20]))
         n_img = int(rng.choice([1, 5, 60, 400]))
         t_rows, p_rows = [], []
@@ -117,3 +117,53 @@ def test_map_random_rows():
             got, ap = yu.mean_average_precision(torch.from_numpy(t).to(dev), torch.from_numpy(p).to(dev), C, thr, return_ap=True)
             assert abs(float(got) - float(want)) <= 1e-6, (trial, thr, float(got), float(want))
             np.testing.assert_allclose(ap.cpu().numpy(), want_ap, atol=1e-6)
+
+
+def test_evaluator_random_shapes(monkeypatch):
+    """MeanAveragePrecision over random grids / boxes / classes / batch splits: update_state as ONE kernel and as three
+    launches must leave identical row buffers, records and ground-truth counts (bit for bit), result() on the counting path
+    and on the radix passes must agree bit for bit, and rows and mAP must equal the oracle evaluator's (NumPy restatement
+    of utils.py:459-496): rows bit-exact, mAP to 1e-6."""
+    from oracle import yolo_oracle as O
+    from yolohot import utils as yu
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(int(os.environ.get("YH_FUZZ_SEED", 4242)))
+    for trial in range(int(os.environ.get("YH_FUZZ_TRIALS_EVAL", 24))):
+        S = int(rng.integers(1, 9))
+        B = int(rng.integers(1, 4))
+        C = int(rng.choice([1, 3, 20, 80]))
+        batches = [int(rng.choice([1, 2, 7, 19, 40])) for _ in range(int(rng.integers(1, 4)))]
+        data = []
+        for k, n in enumerate(batches):
+            yt = F.synth_labels(n, S, B, C, seed=1000 * trial + k, lam=float(rng.choice([0.5, 2.5, 8.0])))
+            yp = F.synth_map_pred(yt, B, C, seed=1000 * trial + k)
+            if rng.random() < 0.3:                                       # tie-heavy confidences
+                yp[..., C] = np.round(yp[..., C] * 8) / 8
+            data.append((yt, yp))
+        oe = O.MeanAveragePrecision(C, B)
+        for yt, yp in data:
+            oe.update_state(yt, yp)
+        want_m = float(oe.result())
+        got = {}
+        for fused in ("1", "0"):
+            monkeypatch.setenv("YH_EVAL_FUSED", fused)
+            ev = yu.MeanAveragePrecision(C, B)
+            for yt, yp in data:
+                ev.update_state(torch.from_numpy(yt).to(dev), torch.from_numpy(yp).to(dev))
+            monkeypatch.delenv("YH_MAP_COUNT", raising=False)
+            m_count = ev.result().clone()
+            monkeypatch.setenv("YH_MAP_COUNT", "0")
+            m_radix = ev.result().clone()
+            monkeypatch.delenv("YH_MAP_COUNT")
+            torch.cuda.synchronize()
+            st = ev._st
+            npred, ntrue = int(st["cursors"][0]), int(st["cursors"][1])
+            got[fused] = (st["pred"][:npred].clone(), st["true"][:ntrue].clone(), st["rec"][:npred].clone(), st["gt"].clone(), m_count)
+            what = f"trial {trial}: S={S} B={B} C={C} batches={batches} fused={fused}"
+            assert torch.equal(m_count.view(torch.int32), m_radix.view(torch.int32)), what
+            assert abs(float(m_count) - want_m) <= 1e-6, (what, float(m_count), want_m)
+            assert np.array_equal(st["pred"][:npred].cpu().numpy(), oe.all_pred_boxes_variable.reshape(-1, 7)[:npred] if npred else np.zeros((0, 7), F32)), what
+            assert np.array_equal(st["true"][:ntrue].cpu().numpy(), oe.all_true_boxes_variable.reshape(-1, 7)[:ntrue] if ntrue else np.zeros((0, 7), F32)), what
+        monkeypatch.delenv("YH_EVAL_FUSED")
+        for x, y in zip(got["1"], got["0"]):
+            assert torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x, y.view(torch.int32) if y.dtype == torch.float32 else y), (trial, S, B, C)
