@@ -160,14 +160,15 @@ YH_API int yh_eval_update(const float *pred_boxes, const int32_t *pred_count,
  * nms_conf_thr - the reference hard-codes 0.5 / 0.4), matches the image (match_iou_thr, utils.py:496)
  * while its kept rows are still in shared memory, and appends rows and records exactly like
  * yh_eval_update (same buffers, cursors and record layout; the results are bit-identical to
- * yh_decode_nms x 2 + yh_eval_update).  Grids of more than 64 cells, or class counts whose tables do
+ * yh_decode_nms x 2 + yh_eval_update).  restart != 0: the evaluator starts over (utils.py:484-486) - the
+ * two cursors and gt_per_class are zeroed on the stream before the kernel.  Grids of more than 64 cells, or class counts whose tables do
  * not fit shared memory, return YH_ERR_UNSUPPORTED: use the three calls.  One launch wins where three
  * are latency - up to about 8,000 VOC-sized images per call on a B200 (33 vs 45 us at 5,000); beyond
  * that the TMA tile kernels behind yh_decode_nms stream the cells faster (85 vs 132 us at 20,000). */
 YH_API int yh_eval_update_state(const float *y_true, const float *y_pred, int64_t n, int S, int B, int C,
                          float nms_iou_thr, float nms_conf_thr, int64_t img_base, float match_iou_thr,
                          float *pred_rows, int64_t pred_capacity, float *true_rows, int64_t true_capacity,
-                         uint64_t *rec, int64_t *cursors, int32_t *gt_per_class, void *stream);
+                         uint64_t *rec, int64_t *cursors, int32_t *gt_per_class, int restart, void *stream);
 
 /* ---- loss: loss.py:120-215 YoloV1Loss.call (+ its autodiff backward) ------------------
  * y_true, y_pred: (n_cells, C+5B) i.e. the (N,S,S,D) tensors flattened over cells.

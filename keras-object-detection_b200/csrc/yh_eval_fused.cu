@@ -227,7 +227,7 @@ using namespace yh;
 extern "C" int yh_eval_update_state(const float *y_true, const float *y_pred, int64_t n, int S, int B, int C, float nms_iou_thr,
                                     float nms_conf_thr, int64_t img_base, float match_iou_thr, float *pred_rows,
                                     int64_t pred_capacity, float *true_rows, int64_t true_capacity, uint64_t *rec,
-                                    int64_t *cursors, int32_t *gt_per_class, void *stream)
+                                    int64_t *cursors, int32_t *gt_per_class, int restart, void *stream)
 {
     NmsCfg cfg;
     int rc = fill_cfg(cfg, S, B, C, nms_iou_thr, nms_conf_thr);
@@ -237,6 +237,12 @@ extern "C" int yh_eval_update_state(const float *y_true, const float *y_pred, in
     if (cfg.M > 64) {
         set_error("eval_update_state: grids of more than 64 cells take the three-launch path (yh_decode_nms x 2 + yh_eval_update)");
         return YH_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (restart) {                    // utils.py:484-486: the first image of an epoch overwrites - cursors and counts start at zero
+        YH_REQUIRE(cursors && gt_per_class, "eval_update_state: null pointer");
+        YH_CUDA(cudaMemsetAsync(cursors, 0, 2 * sizeof(int64_t), st));
+        YH_CUDA(cudaMemsetAsync(gt_per_class, 0, static_cast<size_t>(C) * sizeof(int32_t), st));
     }
     if (n == 0) return YH_OK;
     YH_REQUIRE(y_true && y_pred && cursors && rec && gt_per_class, "eval_update_state: null pointer");
@@ -252,7 +258,6 @@ extern "C" int yh_eval_update_state(const float *y_true, const float *y_pred, in
     a.rec = reinterpret_cast<unsigned long long *>(rec);
     a.gt_per_class = gt_per_class;
     a.n = n; a.img_base = img_base; a.match_thr = match_iou_thr;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int ns = pick_ns(cfg.M);
     if (ns == 2 && C == 20 && B == 2) return launch_eval_state<2, 20, 2>(a, cfg, st);
     if (ns == 1) return launch_eval_state<1, 0, 0>(a, cfg, st);

@@ -66,7 +66,7 @@ def lib():
     L.yh_rows_append.argtypes = [vp, vp, i64, i, i64, vp, i64, vp, vp]
     L.yh_loss.argtypes = [vp, vp, i64, i, i, f, f, vp, vp, vp]
     L.yh_eval_update.argtypes = [vp, vp, vp, vp, i64, i, i64, i, f, vp, i64, vp, i64, vp, vp, vp, vp]
-    L.yh_eval_update_state.argtypes = [vp, vp, i64, i, i, i, f, f, i64, f, vp, i64, vp, i64, vp, vp, vp, vp]
+    L.yh_eval_update_state.argtypes = [vp, vp, i64, i, i, i, f, f, i64, f, vp, i64, vp, i64, vp, vp, vp, i, vp]
     L.yh_map_match.argtypes = [vp, i64, vp, vp, i64, vp, i, f, i, vp, vp, vp, C.c_size_t, vp]
     L.yh_map_reduce.argtypes = [vp, i64, vp, i64, vp, i, vp, vp, vp, C.c_size_t, vp]
     L.yh_map_exchange_bytes.argtypes = [i, i, i64]

@@ -433,8 +433,8 @@ class MeanAveragePrecision:
         self._dev = dev
         M = S * S
         st = self._ensure(dev, n * M)
-        if self.img_idx == 0:                       # utils.py:484-486: first image overwrites
-            st["state"].zero_()
+        restart = self.img_idx == 0                 # utils.py:484-486: first image overwrites
+        if restart:
             st["bound"] = 0
         fused_env = os.environ.get("YH_EVAL_FUSED", "")           # "0" / "1" force a path; default: by batch size
         if (self._nms_true and M <= 64 and yt.data_ptr() % 8 == 0 and yp.data_ptr() % 8 == 0
@@ -447,12 +447,14 @@ class MeanAveragePrecision:
                 rc = _lib.lib().yh_eval_update_state(yt.data_ptr(), yp.data_ptr(), n, S, self._num_boxes, self._num_classes, 0.5, 0.4,
                                                      int(self.img_idx), self._IOU_THR, st["pred"].data_ptr(), st["cap"],
                                                      st["true"].data_ptr(), st["cap"], st["rec"].data_ptr(), st["cursors"].data_ptr(),
-                                                     st["gt"].data_ptr(), stream_ptr(dev))
+                                                     st["gt"].data_ptr(), 1 if restart else 0, stream_ptr(dev))
             if rc != _lib.YH_ERR_UNSUPPORTED:          # (class tables that do not fit shared memory: the three launches below)
-                _lib.check(rc, "update_state")
-                st["bound"] += n * M
+                _lib.check(rc, "update_state")         # (a restart zeroes cursors and counts inside the call: two memsets on
+                st["bound"] += n * M                   # the stream instead of a torch fill launch)
                 self.img_idx += n                        # utils.py:491
                 return
+        if restart:
+            st["state"].zero_()
         key = (n, M)
         bufs = self._cache.get(key)
         if bufs is None:                            # padded NMS outputs of one batch, reused by the next one
@@ -488,7 +490,10 @@ class MeanAveragePrecision:
         if sharded:
             m, self.last_ap = _reduce_sharded(rec, nrec, st["bound"], st["gt"], C_, self._group, self._capacity)
             return m
-        nbytes = int(_lib.lib().yh_workspace_bytes(_lib.YH_OP_MAP_REDUCE, int(rec.shape[0]), 0, 0, C_))
+        wkey = ("ws_bytes", int(rec.shape[0]))
+        nbytes = self._cache.get(wkey)
+        if nbytes is None:
+            nbytes = self._cache[wkey] = int(_lib.lib().yh_workspace_bytes(_lib.YH_OP_MAP_REDUCE, int(rec.shape[0]), 0, 0, C_))
         m, self.last_ap = map_reduce(rec, st["gt"], C_, nrec_dev=nrec, workspace=_workspace(dev, nbytes, self._cache), n_hint=st["bound"])
         return m
 

@@ -56,14 +56,14 @@ def test_argument_errors_need_no_gpu():
     assert L.yh_eval_update(None, None, None, None, 4, 49, 0, 20, 0.5, None, 0, None, 0, None, None, None, None) == _lib.YH_ERR_ARG
     # update_state in one launch: sizes, null pointers, the grids it hands to the three-launch path, alignment
     us = L.yh_eval_update_state
-    assert us(None, None, -1, 7, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, None) == _lib.YH_ERR_ARG
-    assert us(None, None, 4, 7, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, None) == _lib.YH_ERR_ARG
+    assert us(None, None, -1, 7, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, 0, None) == _lib.YH_ERR_ARG
+    assert us(None, None, 4, 7, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, 0, None) == _lib.YH_ERR_ARG
     assert b"null pointer" in L.yh_last_error()
-    assert us(None, None, 4, 9, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, None) == _lib.YH_ERR_UNSUPPORTED
+    assert us(None, None, 4, 9, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, 0, None) == _lib.YH_ERR_UNSUPPORTED
     assert b"three-launch path" in L.yh_last_error()
-    assert us(None, None, 4, 7, 2, 5000, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, None) == _lib.YH_ERR_ARG   # C limit
-    assert us(None, None, 0, 7, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, None) == _lib.YH_OK       # nothing to do
-    assert us(12, 16, 4, 7, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, 8, 8, 8, None) == _lib.YH_ERR_ARG             # y_true not 8-byte aligned
+    assert us(None, None, 4, 7, 2, 5000, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, 0, None) == _lib.YH_ERR_ARG   # C limit
+    assert us(None, None, 0, 7, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, None, None, None, 0, None) == _lib.YH_OK       # nothing to do
+    assert us(12, 16, 4, 7, 2, 20, 0.5, 0.4, 0, 0.5, None, 0, None, 0, 8, 8, 8, 0, None) == _lib.YH_ERR_ARG             # y_true not 8-byte aligned
     assert b"8-byte aligned" in L.yh_last_error()
     assert L.yh_workspace_bytes(_lib.YH_OP_MAP_REDUCE, 100000, 0, 0, 20) >= 2 * 8 * 100000
     assert L.yh_workspace_bytes(_lib.YH_OP_MAP_MATCH, 100000, 0, 0, 20) >= 12 * 100000
